@@ -1,0 +1,371 @@
+"""DeepWalk on the GPU behind genewalk's own API.
+
+Mirrors /root/reference/genewalk/deepwalk.py: ``DeepWalk(graph, walk_length=10, niter=100)`` with
+``get_walks(workers)`` and ``word2vec(...)``, module functions ``get_start_nodes``,
+``run_walks_for_node``, ``run_single_walk`` and ``run_walks(graph, **kwargs)``.  The arithmetic runs
+in libgenewalk_b200.so (hand-written sm_100a CUDA) through the C ABI in include/genewalk_b200.h:
+gw_walk_uniform replaces the Python walk loops (deepwalk.py:50-96,145-200) and
+gw_count_tokens / gw_vocab_rank / gw_alias_build / gw_sgns_init / gw_sgns_train replace
+``gensim.models.Word2Vec`` (deepwalk.py:135-139).  There is no CPU fallback.
+
+Differences a caller can observe (all documented in DESIGN.md):
+  * walks are drawn by a counter-based Philox sampler, not CPython's MT19937; the seed is taken
+    from ``random.getrandbits(64)`` so ``random.seed(...)`` (cli.py:187-189) still makes runs
+    reproducible -- and, unlike the reference, also for ``workers > 1`` (a no-op hint here);
+  * ``self.walks`` is a lazy sequence over device memory (``len``, indexing and iteration behave
+    like the reference's list of lists of node labels);
+  * unsupported Word2Vec settings (sg=0, hs=1, window != 1, sample > 0, min_count > 1) raise
+    instead of silently training something else.
+"""
+import logging
+import random
+import time
+from collections.abc import Sequence
+
+import numpy as np
+
+from . import _lib
+from .csr import GraphCSR, coprime_stride
+from .keyedvectors import NodeVectors, Word2VecModel
+
+logger = logging.getLogger('genewalk.deepwalk')
+
+default_walk_length = 10
+default_niter = 100
+
+
+def _csr_of(graph):
+    """GraphCSR of an nx.MultiGraph (or a GraphCSR / an object carrying one)."""
+    if isinstance(graph, GraphCSR):
+        return graph
+    attrs = getattr(graph, 'graph', None)
+    if isinstance(attrs, dict) and isinstance(attrs.get('_gw_csr'), GraphCSR):
+        return attrs['_gw_csr']
+    return GraphCSR.from_networkx(graph)
+
+
+class WalkCorpus(Sequence):
+    """Lazy list-of-walks view over the device token array.
+
+    Index ``i`` is the walk's position in the reference's serial corpus (node-major: node v owns
+    ``niter*len(graph[v])`` consecutive walks, deepwalk.py:67-70,197); the device stores walks in
+    slot order (see gw_walk_uniform) and position-major (``tokens[k, p]`` = k-th node of slot p).
+    """
+
+    def __init__(self, csr, tokens, niter, stride):
+        self.csr = csr
+        self.tokens = tokens          # torch int32 [L, W] on the device (or numpy after pickling)
+        self.niter = int(niter)
+        self.stride = int(stride)
+        self.A = csr.nnz
+        self._inv = pow(self.stride, -1, self.A) if self.A > 1 else 0
+
+    def __len__(self):
+        return int(self.tokens.shape[1])
+
+    @property
+    def walk_length(self):
+        return int(self.tokens.shape[0])
+
+    def slots_of(self, idx):
+        idx = np.asarray(idx, dtype=np.int64)
+        e, it = idx // self.niter, idx % self.niter
+        r = (e * self._inv) % self.A if self.A > 1 else e
+        return it * self.A + r
+
+    def _labels(self, cols):
+        nodes = self.csr.nodes
+        return [[nodes[t] for t in col if t >= 0] for col in cols]
+
+    def _fetch(self, idx):
+        slots = self.slots_of(idx)
+        if isinstance(self.tokens, np.ndarray):
+            return self.tokens[:, slots].T
+        import torch
+        sl = torch.as_tensor(slots, device=self.tokens.device)
+        return self.tokens.index_select(1, sl).t().cpu().numpy()
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return self._labels(self._fetch(np.arange(*i.indices(len(self)))))
+        n = len(self)
+        if i < 0:
+            i += n
+        if not 0 <= i < n:
+            raise IndexError(i)
+        return self._labels(self._fetch([i]))[0]
+
+    def __iter__(self, chunk=1 << 16):
+        n = len(self)
+        for b in range(0, n, chunk):
+            for w in self._labels(self._fetch(np.arange(b, min(n, b + chunk)))):
+                yield w
+
+    def start_node_ids(self):
+        """Node id of the first node of every walk, in corpus order (cheap: row of the entry)."""
+        self.csr.to_host()
+        return np.repeat(np.repeat(np.arange(self.csr.n), np.diff(self.csr.row_ptr)), self.niter)
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        if not isinstance(self.tokens, np.ndarray):
+            st['tokens'] = self.tokens.cpu().numpy()
+        self.csr.to_host()
+        st['csr'] = GraphCSR(self.csr.nodes, self.csr.row_ptr, self.csr.col_idx)
+        return st
+
+
+class DeepWalk(object):
+    """Perform DeepWalk (node2vec), i.e., unbiased random walk over nodes
+    on an undirected networkx MultiGraph.
+
+    Parameters
+    ----------
+    graph : networkx.MultiGraph
+        A networkx multigraph to be used as the basis for DeepWalk.
+    walk_length : Optional[int]
+        The length of each random walk on the graph. Default: 10
+    niter : Optional[int]
+        The number of iterations for each node to run (this is multiplied by
+        the number of neighbors of the node when determining the overall number
+        of walks to start from a given node). Default: 100
+    seed : Optional[int]
+        64-bit seed of the Philox sampler.  Default: ``random.getrandbits(64)``, so Python's
+        ``random.seed`` governs reproducibility as in the reference.
+
+    Attributes
+    ----------
+    walks : sequence
+        The walks (lazy sequence of lists of node labels).
+    """
+
+    def __init__(self, graph, walk_length=default_walk_length, niter=default_niter, seed=None):
+        self.graph = graph
+        self.walks = []
+        self.wl = walk_length
+        self.niter = niter
+        self.model = None
+        self.seed = seed
+        self._csr = None
+        self.timings = {}
+
+    # ------------------------------------------------------------------------------------------
+    def _get_csr(self):
+        if self._csr is None:
+            self._csr = _csr_of(self.graph)
+        return self._csr
+
+    def get_walks(self, workers=1, stride=None):
+        """Generates walks (sentences) sampled by an (unbiased) random walk over the graph.
+
+        ``workers`` is accepted for API compatibility (the GPU runs one thread per walk).
+        ``stride`` selects the storage-slot permutation (None: golden-ratio stride coprime to A,
+        which spreads the start nodes of concurrently trained walks; 1: plain iteration-major).
+        """
+        import torch
+        _lib.require_cuda()
+        logger.info('Running random walks...')
+        start = time.time()
+        if int(self.wl) < 1 or int(self.niter) < 1:
+            raise ValueError('walk_length and niter must be positive')
+        seed = self.seed if self.seed is not None else random.getrandbits(64)
+        self._walk_seed = int(seed) & (2 ** 64 - 1)
+        csr = self._get_csr().to_device()
+        A = csr.nnz
+        if A == 0:
+            self.walks = []
+            return
+        W = int(self.niter) * A
+        stride = coprime_stride(A) if stride is None else int(stride)
+        tokens = torch.empty((int(self.wl), W), dtype=torch.int32, device=csr.d_row_ptr.device)
+        _lib.call('gw_walk_uniform', csr.n, A, _lib.ptr(csr.d_row_ptr), _lib.ptr(csr.d_col_idx),
+                  int(self.niter), int(self.wl), self._walk_seed, stride, 0, W, _lib.ptr(tokens),
+                  _lib.stream_ptr())
+        self.walks = WalkCorpus(csr, tokens, self.niter, stride)
+        end = time.time()
+        self.timings['get_walks_enqueue_s'] = end - start
+        logger.info('Running random walks done in %.2fs' % (end - start))
+
+    # ------------------------------------------------------------------------------------------
+    def _device_corpus(self):
+        """(csr-like node list, n, tokens [L, W] device tensor) of ``self.walks``."""
+        import torch
+        if isinstance(self.walks, WalkCorpus):
+            tok = self.walks.tokens
+            if isinstance(tok, np.ndarray):
+                tok = torch.from_numpy(tok).cuda()
+            return self.walks.csr.nodes, self.walks.csr.n, tok
+        # a plain list of lists of labels (what the reference stores): encode, pad ragged with -1
+        walks = list(self.walks)
+        if not walks:
+            raise RuntimeError('you must first build vocabulary before training the model')
+        nodes, index = [], {}
+        L = max(len(w) for w in walks)
+        arr = np.full((L, len(walks)), -1, dtype=np.int32)
+        for p, w in enumerate(walks):
+            for k, t in enumerate(w):
+                i = index.get(t)
+                if i is None:
+                    i = index[t] = len(nodes)
+                    nodes.append(t)
+                arr[k, p] = i
+        return nodes, len(nodes), torch.from_numpy(arr).cuda()
+
+    def word2vec(self, sg=1, vector_size=8, window=1, min_count=1, negative=5,
+                 workers=1, sample=0, **kwargs):
+        """Set the model based on Word2Vec (skip-gram with negative sampling, trained on the GPU).
+
+        Same signature and defaults as the reference (deepwalk.py:98-99); the remaining gensim
+        defaults can be overridden by keyword: ``epochs`` (5), ``alpha`` (0.025), ``min_alpha``
+        (0.0001), ``seed`` (1, weight init), ``ns_exponent`` (0.75), ``batch_words`` (10000),
+        ``hs`` (0).  GPU-only knobs: ``max_threads`` (0 = one resident wave; the number of walks
+        trained concurrently under Hogwild) and ``sgns_seed`` (Philox key of the negative draws).
+        """
+        import torch
+        _lib.require_cuda()
+        epochs = int(kwargs.pop('epochs', 5))
+        alpha = float(kwargs.pop('alpha', 0.025))
+        min_alpha = float(kwargs.pop('min_alpha', 0.0001))
+        init_seed = int(kwargs.pop('seed', 1))
+        ns_exponent = float(kwargs.pop('ns_exponent', 0.75))
+        batch_words = int(kwargs.pop('batch_words', 10000))
+        hs = int(kwargs.pop('hs', 0))
+        max_threads = int(kwargs.pop('max_threads', 0))
+        sgns_seed = kwargs.pop('sgns_seed', None)
+        if kwargs:
+            raise TypeError('word2vec() got unexpected keyword arguments %s' % sorted(kwargs))
+        if sg != 1:
+            raise ValueError('only skip-gram (sg=1) is implemented; GeneWalk always uses sg=1')
+        if hs != 0 or negative <= 0:
+            raise ValueError('only negative sampling (hs=0, negative>0) is implemented')
+        if window != 1:
+            raise ValueError('only window=1 is implemented; GeneWalk always uses window=1')
+        if sample != 0:
+            raise ValueError('sub-sampling (sample>0) is not implemented; GeneWalk uses sample=0')
+        if min_count not in (0, 1):
+            raise ValueError('min_count>1 is not implemented; GeneWalk uses min_count=1')
+        logger.info('Generating node vectors...')
+        start = time.time()
+        nodes, n, tokens = self._device_corpus()
+        L, W = int(tokens.shape[0]), int(tokens.shape[1])
+        d = int(vector_size)
+        dev = tokens.device
+        st = _lib.stream_ptr()
+        if sgns_seed is None:
+            sgns_seed = (getattr(self, '_walk_seed', 0) ^ 0x5DEECE66D5DEECE6) & (2 ** 64 - 1)
+        counts = torch.empty(n, dtype=torch.int64, device=dev)
+        rank_of_node = torch.empty(n, dtype=torch.int32, device=dev)
+        node_of_rank = torch.empty(n, dtype=torch.int32, device=dev)
+        n_vocab = torch.zeros(1, dtype=torch.int32, device=dev)
+        alias = torch.empty((n, 2), dtype=torch.int32, device=dev)   # gw_alias_entry[n]
+        syn0 = torch.empty((n, d), dtype=torch.float32, device=dev)
+        syn1neg = torch.empty((n, d), dtype=torch.float32, device=dev)
+        # gensim init_weights: rows of default_rng(seed).random((V, d), float32); V <= n and the
+        # generator fills row-major, so the first V rows of an (n, d) draw are the (V, d) draw
+        rng = np.random.default_rng(seed=init_seed)
+        rows = rng.random((n, d), dtype=np.float32)
+        rows *= 2.0
+        rows -= 1.0
+        rows /= d
+        rng_rows = torch.from_numpy(rows).to(dev)
+        _lib.call('gw_count_tokens', _lib.ptr(tokens), L * W, n, _lib.ptr(counts), st)
+        _lib.call('gw_vocab_rank', n, _lib.ptr(counts), _lib.ptr(rank_of_node),
+                  _lib.ptr(node_of_rank), _lib.ptr(n_vocab), st)
+        _lib.call('gw_alias_build', n, _lib.ptr(counts), ns_exponent, _lib.ptr(alias), st)
+        _lib.call('gw_sgns_init', n, d, _lib.ptr(rank_of_node), _lib.ptr(rng_rows), _lib.ptr(syn0),
+                  _lib.ptr(syn1neg), st)
+        job_walks = max(1, batch_words // max(L, 1))
+        _lib.call('gw_sgns_train', n, d, _lib.ptr(tokens), W, L, int(window), int(negative), epochs,
+                  0, epochs, alpha, min_alpha, job_walks, _lib.ptr(alias), _lib.ptr(syn0),
+                  _lib.ptr(syn1neg), int(sgns_seed), max_threads, st)
+        # results -> host (the only synchronisation of the replicate)
+        nv = int(n_vocab.item())
+        order = node_of_rank[:nv].long()
+        vectors = syn0.index_select(0, order).cpu().numpy()
+        out_layer = syn1neg.index_select(0, order).cpu().numpy()
+        cnt = counts.index_select(0, order).cpu().numpy()
+        order_h = order.cpu().numpy()
+        wv = NodeVectors([nodes[i] for i in order_h], vectors, counts=cnt)
+        wv.node_ids = order_h.astype(np.int32)   # row r of wv.vectors is graph node node_ids[r]
+        self.model = Word2VecModel(wv, syn1neg=out_layer, sg=1, vector_size=d, window=window,
+                                   min_count=min_count, negative=negative, sample=sample,
+                                   epochs=epochs, alpha=alpha, min_alpha=min_alpha, seed=init_seed,
+                                   ns_exponent=ns_exponent, corpus_count=W, workers=workers)
+        end = time.time()
+        self.timings['word2vec_s'] = end - start
+        logger.info('Generating node vectors done in %.2fs' % (end - start))
+
+
+# ---------------------------------------------------------------------------------------------
+# module-level functions of the reference API
+# ---------------------------------------------------------------------------------------------
+def get_start_nodes(graph, niter):
+    """Start node of every walk, corpus order: each node ``niter * len(graph[node])`` times
+    (deepwalk.py:170-174)."""
+    csr = _csr_of(graph)
+    csr.to_host()
+    deg = np.diff(csr.row_ptr)
+    return [csr.nodes[v] for v in np.repeat(np.arange(csr.n), deg * int(niter))]
+
+
+def run_walks_for_node(node, graph, niter, walk_length, seed=None):
+    """Run all random walks starting from a given node (deepwalk.py:177-200)."""
+    import torch
+    _lib.require_cuda()
+    csr = _csr_of(graph).to_device()
+    csr.to_host()
+    v = csr.index[node]
+    b, e = int(csr.row_ptr[v]), int(csr.row_ptr[v + 1])
+    if e == b:
+        return []
+    seed = random.getrandbits(64) if seed is None else int(seed)
+    A, it_n = csr.nnz, int(niter)
+    # plain iteration-major slots (stride 1): walk (e, it) sits in slot it*A + e
+    out = []
+    buf = torch.empty((int(walk_length), e - b), dtype=torch.int32, device=csr.d_row_ptr.device)
+    cols = []
+    for it in range(it_n):
+        _lib.call('gw_walk_uniform', csr.n, A, _lib.ptr(csr.d_row_ptr), _lib.ptr(csr.d_col_idx),
+                  it_n, int(walk_length), seed, 1, it * A + b, it * A + e, _lib.ptr(buf),
+                  _lib.stream_ptr())
+        cols.append(buf.t().cpu().numpy().copy())
+    arr = np.stack(cols, axis=1).reshape(-1, int(walk_length))   # entry-major, iteration-minor
+    for row in arr:
+        out.append([csr.nodes[t] for t in row])
+    return out
+
+
+def run_single_walk(start_node, graph, length, seed=None):
+    """Run a single random walk on a graph from a given start node (deepwalk.py:145-167)."""
+    walks = run_walks_for_node(start_node, graph, 1, length, seed=seed)
+    if not walks:
+        raise IndexError('Cannot choose from an empty sequence')   # random.choice on no neighbours
+    return walks[0]
+
+
+def run_walks(graph, **kwargs):
+    """Run random walks and get node vectors on a given graph.
+
+    Parameters
+    ----------
+    graph : networkx.MultiGraph
+        The graph on which random walks are going to be run and node vectors
+        calculated.
+    **kwargs
+        Key word arguments passed as the arguments of the DeepWalk constructor,
+        as well as the get_walks method and the word2vec method. See the
+        DeepWalk class documentation for more information on these.
+
+    Returns
+    -------
+    :py:class:`genewalk_b200.deepwalk.DeepWalk`
+        A DeepWalk instance whose walks attribute contains the random walks produced on the graph
+        and whose ``model.wv`` holds the node vectors.
+    """
+    dw_args = {'walk_length': kwargs.pop('walk_length', default_walk_length),
+               'niter': kwargs.pop('niter', default_niter),
+               'seed': kwargs.pop('walk_seed', None)}
+    DW = DeepWalk(graph, **dw_args)
+    DW.get_walks(kwargs.get('workers', 1))
+    DW.word2vec(**kwargs)
+    return DW
