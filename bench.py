@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- GeneWalk hot-path benchmark (contract: see the task prompt / DESIGN.md section 6).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--scale S]
+
+A "step" is ONE node_vectors replicate of the hot path on the human-scale synthetic gene-GO network
+(BASELINE.json configs[1]: ~20k genes + ~18k GO terms, ~1M edges; reference defaults
+walk_length=10, niter=100, vector_size=8, window=1, negative=5, epochs=5): random walks from every
+node (W = 100*A walks) followed by the 5 SGNS epochs over them (5 * 18 * W pairs).
+metric = SGNS (centre, context) pairs trained per second of whole-replicate time (walk generation,
+vocabulary, alias table and init included).
+
+  value   inputs (CSR) already resident in HBM, results left on the device
+  e2e     the same replicate through the public API run_walks(nx.MultiGraph): CSR extraction from
+          networkx, host->device copies, training, device->host copy of the vectors
+  N > 1   every rank runs its own replicate (the path shards by replicate); one NCCL
+          all-gather of the per-replicate gene-GO similarity vector closes each step (weak scaling)
+  --impl reference   the reference's CPU path for the same step restated in C (oracle/, gensim-
+          faithful SGNS, OpenMP Hogwild on all host cores) on a bounded sample of the same corpus
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NITER, WL, D, K, EPOCHS = 100, 10, 8, 5, 5
+BYTES_PER_PAIR = 4 * D * (2 * K + 4) + 8 + 8 * K      # 496 at d=8, K=5
+BYTES_PER_STEP = 16                                     # walk step
+METRIC = 'SGNS pairs/s over a node_vectors replicate (walks + 5 SGNS epochs)'
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockMonitor(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._halt = index, [], threading.Event()
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                f = [x.strip() for x in out.split(',')]
+                if len(f) >= 7:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=6)
+        sm = [float(s[0]) for s in self.samples if s[0].replace('.', '').isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if s[3 + i] == 'Active'})
+        return {'sm_mhz': float(np.median(sm)) if sm else None,
+                'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'samples': len(self.samples)}
+
+
+def build_inputs(scale):
+    from tests import graphs
+    ng, ngo = int(20000 * scale), int(18000 * scale)
+    n, u, v, is_go = graphs.human_scale_edges(seed=2, n_genes=ng, n_go=ngo,
+                                              n_gene_edges=int(700000 * scale),
+                                              n_annot=int(250000 * scale), n_isa=int(50000 * scale),
+                                              n_modules=max(4, int(500 * scale)))
+    return graphs, n, u, v, is_go, ng
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_sample_rate(row_ptr, col_idx, threads, target_s=15.0):
+    """Oracle (gensim-faithful C restatement, OpenMP) on a bounded sample of the workload's corpus:
+    the first `m` walks of the reference's corpus order, all 5 epochs.  Returns (pairs/s, text)."""
+    from oracle import lib as olib
+    n = len(row_ptr) - 1
+    W = NITER * int(row_ptr[-1])
+
+    def run(m):
+        t0 = time.perf_counter()
+        tok = olib.walk_uniform(row_ptr, col_idx, NITER, WL, 12345, 0, 0, m)
+        olib.word2vec_gensim_like(tok, n, d=D, K=K, epochs=EPOCHS, nthreads=threads)
+        return time.perf_counter() - t0
+    pilot = min(W, 20000 * max(1, threads))
+    dt = run(pilot)
+    rate = pilot * 2 * (WL - 1) * EPOCHS / dt
+    m = int(min(W, max(pilot, rate * target_s / (2 * (WL - 1) * EPOCHS))))
+    if m > pilot:
+        dt = run(m)
+    else:
+        m = pilot
+    pairs = m * 2 * (WL - 1) * EPOCHS
+    return pairs / dt, ('first %d of %d walks of the corpus (reference order), %d epochs = %.1f M '
+                        'pairs in %.1f s' % (m, W, EPOCHS, pairs / 1e6, dt))
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    graphs, n, u, v, is_go, ng = build_inputs(args.scale)
+    row_ptr, col_idx = graphs.csr_from_edges_numpy(n, u, v)
+    from oracle import lib as olib
+    threads = olib.lib().gwo_max_threads()
+    vals, sample = [], ''
+    t_all = time.perf_counter()
+    for i in range(args.warmup + args.steps):
+        rate, sample = cpu_sample_rate(row_ptr, col_idx, threads,
+                                       target_s=min(15.0, 120.0 / max(1, args.warmup + args.steps)))
+        if i >= args.warmup:
+            vals.append(rate)
+    value = float(np.mean(vals))
+    A = int(row_ptr[-1])
+    pairs_step = NITER * A * 2 * (WL - 1) * EPOCHS
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'pairs/s',
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': 1e3 * pairs_step / value, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(n, len(u), A, args.scale),
+            'cpu_baseline': {'value': value, 'unit': 'pairs/s', 'cores': threads, 'kind': 'port',
+                             'sample': sample},
+            'e2e': {'value': value, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0,
+                    'd2h_bytes_per_step': 0},
+            'note': 'ms_per_step is the full-replicate time extrapolated linearly from the sample; '
+                    'gensim is not installable here, the C oracle restates it (oracle/gw_oracle.c)',
+            'wall_s': time.perf_counter() - t_all}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n, n_edges, A, scale):
+    return {'workload': 'human-scale synthetic gene-GO network, node_vectors replicate '
+                        '(BASELINE.json configs[1])',
+            'nodes': n, 'edges': n_edges, 'adjacency_entries': A, 'walks': NITER * A,
+            'walk_length': WL, 'niter': NITER, 'vector_size': D, 'window': 1, 'negative': K,
+            'epochs': EPOCHS, 'pairs_per_step': NITER * A * 2 * (WL - 1) * EPOCHS,
+            'scale': scale,
+            'l2': 'token stream (%.1f GB) >> 126 MB L2; embedding tables are rebuilt every step'
+                  % (NITER * A * WL * 4 / 1e9)}
+
+
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from genewalk_b200 import _lib
+    from genewalk_b200.csr import GraphCSR
+    from genewalk_b200.deepwalk import DeepWalk, run_walks
+    from genewalk_b200.perform_statistics import GeneWalk
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    _lib.require_cuda()
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    graphs, n, u, v, is_go, ng = build_inputs(args.scale)
+    mg, genes = graphs.edges_to_networkx(n, u, v, is_go, ng)
+    csr = GraphCSR.from_networkx(mg).to_device()
+    A = csr.nnz
+    W = NITER * A
+    pairs_step = W * 2 * (WL - 1) * EPOCHS
+    gw = GeneWalk(mg, genes, [], np.zeros(1, np.float32), gene_id_type='custom')
+    pairs = gw.collect_pairs()
+    d_pg = torch.from_numpy(pairs['pair_gene'].astype(np.int32)).cuda()
+    d_po = torch.from_numpy(pairs['pair_go'].astype(np.int32)).cuda()
+    m_pairs = int(d_po.numel())
+    gathered = [torch.empty(m_pairs, dtype=torch.float32, device='cuda') for _ in range(world)]
+    st = _lib.stream_ptr()
+    train_events = []
+
+    def hook(ep, when):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        train_events.append((ep, when, e))
+
+    def device_step(step, timed):
+        seed = (1 + step) * 1000003 + rank
+        dw = DeepWalk(csr, WL, NITER, seed=seed)
+        w0 = torch.cuda.Event(enable_timing=True); w1 = torch.cuda.Event(enable_timing=True)
+        w0.record()
+        dw.get_walks()
+        w1.record()
+        dv = dw.train_device(vector_size=D, negative=K, epochs=EPOCHS, max_threads=args.max_threads,
+                             epoch_hook=hook if timed else None)
+        # the replicate's product in the pipeline: gene-GO similarities (fixed length), exchanged
+        sims = torch.empty(m_pairs, dtype=torch.float32, device='cuda')
+        _lib.call('gw_cosine_pairs', D, _lib.ptr(dv['syn0']), m_pairs, _lib.ptr(d_pg),
+                  _lib.ptr(d_po), _lib.ptr(sims), st)
+        if world > 1:
+            dist.all_gather(gathered, sims)
+        return (w0, w1), dv, sims
+
+    # ---- value: device-resident ------------------------------------------------------------
+    for i in range(args.warmup):
+        device_step(i, False)
+    barrier()
+    mon = ClockMonitor(local)
+    mon.start()
+    launches0 = _lib.launch_count()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    walk_ev = []
+    for i in range(args.steps):
+        ev, dv, sims = device_step(args.warmup + i, True)
+        walk_ev.append(ev)
+    t1.record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    clocks = mon.stop()
+    ms = t0.elapsed_time(t1)
+    t_ms = torch.tensor([ms], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+    value = world * pairs_step * args.steps / (ms_max / 1e3)
+    # dominant kernel: one SGNS epoch launch
+    befores = [e for ep, when, e in train_events if when == 'before']
+    afters = [e for ep, when, e in train_events if when == 'after']
+    k_ms = [b.elapsed_time(a) for b, a in zip(befores, afters)]
+    k_avg = float(np.mean(k_ms)) if k_ms else float('nan')
+    walk_ms = float(np.mean([a.elapsed_time(b) for a, b in walk_ev]))
+    pairs_launch = W * 2 * (WL - 1)
+    achieved = BYTES_PER_PAIR * pairs_launch / (k_avg / 1e3) / 1e9
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'sgns_train_traffic.json')) as f:
+            traffic = json.load(f).get('dram_bytes_per_launch')
+    except Exception:
+        pass
+
+    # ---- e2e: public API with host inputs ---------------------------------------------------
+    barrier()
+    h2d = csr.row_ptr.nbytes + csr.col_idx.nbytes + n * D * 4
+    d2h = 0
+    for i in range(min(args.warmup, 1)):
+        run_walks(mg, vector_size=D, walk_seed=7 + i, max_threads=args.max_threads)
+    barrier()
+    e0 = time.perf_counter()
+    for i in range(args.steps):
+        dw = run_walks(mg, vector_size=D, walk_seed=100 + i * world + rank,
+                       max_threads=args.max_threads)
+        wv = dw.model.wv
+        d2h = wv.vectors.nbytes + dw.model.syn1neg.nbytes + wv.counts.nbytes + wv.node_ids.nbytes
+        del dw
+    barrier()
+    e_s = time.perf_counter() - e0
+    t_e = torch.tensor([e_s], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = world * pairs_step * args.steps / float(t_e.item())
+
+    line = None
+    if rank == 0:
+        line = {'metric': METRIC, 'value': value, 'unit': 'pairs/s', 'n_gpus': world,
+                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_max / args.steps,
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+                'data': 'synthetic', 'config': workload_config(n, len(u), A, args.scale),
+                'clocks': clocks,
+                'e2e': {'value': e2e_value, 'unit': 'pairs/s', 'h2d_bytes_per_step': int(h2d),
+                        'd2h_bytes_per_step': int(d2h), 'ms_per_step': 1e3 * float(t_e.item()) / args.steps},
+                'gpu_launches': int(launches),
+                'roofline': {'kernel': 'sgns_train_kernel<8,5> (one epoch per launch)',
+                             'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                             'frac': achieved / peak, 'traffic': traffic,
+                             'peak_source': 'measured (MEASURED_PEAKS.json hbm_gbs)' if peaks else 'fallback',
+                             'algorithmic_bytes_per_pair': BYTES_PER_PAIR,
+                             'pairs_per_launch': pairs_launch, 'avg_launch_ms': k_avg,
+                             'note': 'tables are L2-resident by design: the algorithmic bytes are '
+                                     'L2 sector traffic; HBM carries only the token stream'},
+                'walk': {'steps_per_s': W * (WL - 1) / (walk_ms / 1e3), 'ms': walk_ms,
+                         'achieved_gbs': BYTES_PER_STEP * W * (WL - 1) / (walk_ms / 1e3) / 1e9},
+                'sgns_kernel_pairs_per_s': pairs_launch / (k_avg / 1e3),
+                'max_threads': args.max_threads}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import lib as olib
+        csr.to_host()
+        threads = olib.lib().gwo_max_threads()
+        rate, sample = cpu_sample_rate(csr.row_ptr, csr.col_idx, threads)
+        line['cpu_baseline'] = {'value': rate, 'unit': 'pairs/s', 'cores': threads, 'kind': 'port',
+                                'sample': sample}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--scale', type=float, default=1.0, help='shrink the workload (tests only)')
+    ap.add_argument('--max-threads', type=int, default=0, dest='max_threads')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == 'ours' and args.scale == 1.0:
+        print('warning: fewer than 3 warm-up steps', file=sys.stderr)
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

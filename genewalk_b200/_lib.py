@@ -68,8 +68,15 @@ def load():
         fn.restype = ctypes.c_int
     lib.gw_last_error.argtypes = []
     lib.gw_last_error.restype = ctypes.c_char_p
+    lib.gw_launch_count.argtypes = []
+    lib.gw_launch_count.restype = ctypes.c_longlong
     _lib = lib
     return lib
+
+
+def launch_count():
+    """Kernels launched by libgenewalk_b200 since load."""
+    return int(load().gw_launch_count())
 
 
 def last_error():

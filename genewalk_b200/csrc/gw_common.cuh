@@ -20,6 +20,14 @@ void set_error(const char *fmt, ...);
         }                                                                                      \
     } while (0)
 
+// after every kernel launch: count it (gw_launch_count) and surface launch-configuration errors
+void count_launch();
+#define GW_LAUNCH_OK()                       \
+    do {                                     \
+        gw::count_launch();                  \
+        GW_CUDA_OK(cudaGetLastError());      \
+    } while (0)
+
 #define GW_REQUIRE(cond, ...)                  \
     do {                                       \
         if (!(cond)) {                         \

@@ -94,17 +94,17 @@ extern "C" int gw_config_model(int32_t n, const int32_t *degrees, int64_t S, uin
     GW_CUDA_OK(t_owner.alloc(sizeof(uint32_t) * (size_t)S, s));
     const int blocks = ceil_div(n, 256);
     widen_degrees_kernel<<<blocks, 256, 0, s>>>(n, degrees, t_start.as<int64_t>());
-    GW_CUDA_OK(cudaGetLastError());
+    GW_LAUNCH_OK();
     GW_TRY(scan_exclusive_i64(t_start.as<int64_t>(), t_start.as<int64_t>(), n, nullptr, s));
     stub_keys_kernel<<<num_sms() * 8, 256, 0, s>>>(n, degrees, t_start.as<int64_t>(), (uint32_t)seed,
                                                   (uint32_t)(seed >> 32), t_keys.as<uint64_t>(),
                                                   t_owner.as<uint32_t>());
-    GW_CUDA_OK(cudaGetLastError());
+    GW_LAUNCH_OK();
     GW_TRY(radix_sort_u64(t_keys.as<uint64_t>(), t_owner.as<uint32_t>(), S, 64, s));
     const int64_t half = S / 2;
     pair_halves_kernel<<<(unsigned)ceil_div<int64_t>(half, 256), 256, 0, s>>>(half, t_owner.as<uint32_t>(),
                                                                             edge_u, edge_v);
-    GW_CUDA_OK(cudaGetLastError());
+    GW_LAUNCH_OK();
     return GW_OK;
 }
 
@@ -129,17 +129,17 @@ extern "C" int gw_csr_from_edges(int32_t n, int64_t m, const int32_t *u, const i
     GW_CUDA_OK(t_flag.alloc(sizeof(int64_t) * (size_t)count, s));
     GW_CUDA_OK(t_nnz.alloc(sizeof(int64_t), s));
     edge_keys_kernel<<<(unsigned)ceil_div<int64_t>(m, 256), 256, 0, s>>>(m, n, u, v, t_keys.as<uint64_t>());
-    GW_CUDA_OK(cudaGetLastError());
+    GW_LAUNCH_OK();
     int bits = 1;
     while (bits < 64 && ((uint64_t)1 << bits) < (uint64_t)n * (uint64_t)n) ++bits;
     GW_TRY(radix_sort_u64(t_keys.as<uint64_t>(), nullptr, count, bits, s));
     const unsigned blocks = (unsigned)ceil_div<int64_t>(count, 256);
     unique_flags_kernel<<<blocks, 256, 0, s>>>(count, t_keys.as<uint64_t>(), t_flag.as<int64_t>());
-    GW_CUDA_OK(cudaGetLastError());
+    GW_LAUNCH_OK();
     GW_TRY(scan_exclusive_i64(t_flag.as<int64_t>(), t_flag.as<int64_t>(), count, t_nnz.as<int64_t>(), s));
     emit_csr_kernel<<<blocks, 256, 0, s>>>(count, n, t_keys.as<uint64_t>(), t_flag.as<int64_t>(),
                                           t_nnz.as<int64_t>(), row_ptr, col_idx);
-    GW_CUDA_OK(cudaGetLastError());
+    GW_LAUNCH_OK();
     GW_CUDA_OK(cudaMemcpyAsync(nnz_out_host, t_nnz.ptr, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     GW_CUDA_OK(cudaStreamSynchronize(s));
     return GW_OK;

@@ -5,6 +5,8 @@
 #include <math.h>
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "gw_common.cuh"
 
 namespace gw {
@@ -19,6 +21,11 @@ void set_error(const char *fmt, ...)
     va_end(ap);
 }
 const char *last_error() { return g_err; }
+
+// kernels launched by this library since load (a statistic for bench.py's gpu_launches)
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launches() { return g_launches.load(std::memory_order_relaxed); }
 
 // =============================================================================================
 // scan: tiles of 256 threads x 8 items, recursive over the tile totals
@@ -132,15 +139,15 @@ static int scan_impl(const T *in, T *out, int64_t count, T *total, T identity, O
     T *off = tot + tiles;
     scan_tile_kernel<T, Op, kReverse, kInclusive>
         <<<(unsigned)tiles, kScanThreads, 0, s>>>(in, out, count, tot, identity, op);
-    GW_CUDA_OK(cudaGetLastError());
+    GW_LAUNCH_OK();
     if (tiles > 1) {
         // exclusive scan of the tile totals (recursion depth <= 3 for any count < 2^33)
         GW_TRY((scan_impl<T, Op, false, false>(tot, off, tiles, nullptr, identity, op, s)));
         scan_add_offsets_kernel<T, Op, kReverse><<<(unsigned)tiles, kScanThreads, 0, s>>>(out, count, off, op);
-        GW_CUDA_OK(cudaGetLastError());
+        GW_LAUNCH_OK();
         if (total) {
             store_total_kernel<T, Op><<<1, 1, 0, s>>>(off + tiles - 1, tot + tiles - 1, total, op);
-            GW_CUDA_OK(cudaGetLastError());
+            GW_LAUNCH_OK();
         }
     } else if (total) {
         GW_CUDA_OK(cudaMemcpyAsync(total, tot, sizeof(T), cudaMemcpyDeviceToDevice, s));
@@ -285,7 +292,7 @@ static int radix_sort_impl(K *keys, uint32_t *vals, int64_t count, int bits, cud
     for (int p = 0; p < passes; ++p) {
         const int shift = p * 8;
         radix_hist_kernel<K><<<(unsigned)tiles, kSortThreads, 0, s>>>(kin, count, shift, hist, tiles);
-        GW_CUDA_OK(cudaGetLastError());
+        GW_LAUNCH_OK();
         GW_TRY(scan_exclusive_u32(hist, hist, 256 * tiles, nullptr, s));
         if (vals)
             radix_scatter_kernel<K, true><<<(unsigned)tiles, kSortThreads, 0, s>>>(
@@ -293,7 +300,7 @@ static int radix_sort_impl(K *keys, uint32_t *vals, int64_t count, int bits, cud
         else
             radix_scatter_kernel<K, false><<<(unsigned)tiles, kSortThreads, 0, s>>>(
                 kin, nullptr, kout, nullptr, count, shift, hist, tiles);
-        GW_CUDA_OK(cudaGetLastError());
+        GW_LAUNCH_OK();
         K *t = kin; kin = kout; kout = t;
         uint32_t *u = vin; vin = vout; vout = u;
     }
@@ -319,6 +326,7 @@ int radix_sort_u32(uint32_t *keys, uint32_t *vals, int64_t count, int bits, cuda
 
 // ---- C ABI: housekeeping --------------------------------------------------------------------
 extern "C" int gw_version(void) { return GW_VERSION; }
+extern "C" long long gw_launch_count(void) { return gw::launches(); }
 extern "C" const char *gw_last_error(void) { return gw::last_error(); }
 extern "C" int gw_device_count(void)
 {

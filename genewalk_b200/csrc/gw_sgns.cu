@@ -275,7 +275,7 @@ template <int D> __device__ __forceinline__ void load_row(const float *p, float 
     }
 }
 
-// sequential-order, unfused dot product: identical rounding to the oracle (gw_oracle.c pair_update)
+// sequential-order, unfused dot product: identical rounding to the CPU oracle used by the tests
 template <int D> __device__ __forceinline__ float dot_row(const float (&a)[D], const float (&b)[D])
 {
     float f = 0.0f;
@@ -411,14 +411,19 @@ static int launch_train(const TrainParams &P, int64_t max_threads, cudaStream_t 
     GW_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sgns_train_kernel<D, KT>,
                                                              kTrainThreads, 0));
     if (per_sm < 1) per_sm = 1;
-    int64_t threads = (int64_t)num_sms() * per_sm * kTrainThreads;  // one resident wave, persistent
+    const int sms = num_sms();
+    int64_t threads = (int64_t)sms * per_sm * kTrainThreads;  // one resident wave, persistent
     if (max_threads > 0 && max_threads < threads) threads = max_threads;
     if (threads > P.W) threads = P.W;
+    // `threads` walks are in flight at any time (the Hogwild staleness knob).  Below one full
+    // CTA per SM the walks are spread over all SMs in 64-thread CTAs so that every SM's LSU/L1
+    // path carries part of the gather/reduction traffic.
     int block = kTrainThreads;
+    if (threads < (int64_t)sms * kTrainThreads) block = 64;
     if (threads < block) block = (int)threads;
     const int64_t grid = ceil_div<int64_t>(threads, block);
     sgns_train_kernel<D, KT><<<(unsigned)grid, block, 0, s>>>(P);
-    GW_CUDA_OK(cudaGetLastError());
+    GW_LAUNCH_OK();
     return GW_OK;
 }
 
@@ -449,7 +454,7 @@ extern "C" int gw_count_tokens(const int32_t *tokens, int64_t count, int32_t n, 
         count_tokens_global_kernel<<<sms * 8, 256, 0, s>>>(
             tokens, count, reinterpret_cast<unsigned long long *>(counts));
     }
-    GW_CUDA_OK(cudaGetLastError());
+    GW_LAUNCH_OK();
     return GW_OK;
 }
 
@@ -464,12 +469,12 @@ extern "C" int gw_vocab_rank(int32_t n, const int64_t *counts, int32_t *rank_of_
     GW_CUDA_OK(tv.alloc(sizeof(uint32_t) * (size_t)n, s));
     const int blocks = ceil_div(n, 256);
     vocab_keys_kernel<<<blocks, 256, 0, s>>>(n, counts, tk.as<uint64_t>(), tv.as<uint32_t>());
-    GW_CUDA_OK(cudaGetLastError());
+    GW_LAUNCH_OK();
     GW_TRY(radix_sort_u64(tk.as<uint64_t>(), tv.as<uint32_t>(), n, 40, s));
     GW_CUDA_OK(cudaMemsetAsync(n_vocab, 0, sizeof(int32_t), s));
     vocab_finish_kernel<<<blocks, 256, 0, s>>>(n, tk.as<uint64_t>(), tv.as<uint32_t>(), rank_of_node,
                                                node_of_rank, n_vocab);
-    GW_CUDA_OK(cudaGetLastError());
+    GW_LAUNCH_OK();
     return GW_OK;
 }
 
@@ -501,18 +506,18 @@ extern "C" int gw_alias_build(int32_t n, const int64_t *counts, double power, gw
     int64_t *n_light = reinterpret_cast<int64_t *>(w_total + 3);
     const int blocks = ceil_div(n, 256);
     alias_weights_kernel<<<blocks, 256, 0, s>>>(n, counts, power, power == 0.75 ? 1 : 0, w);
-    GW_CUDA_OK(cudaGetLastError());
+    GW_LAUNCH_OK();
     GW_TRY(scan_exclusive_f64(w, q /*scratch*/, n, w_total, s));
     alias_split_kernel<<<blocks, 256, 0, s>>>(n, w, w_total, q, is_light, ql, qh);
-    GW_CUDA_OK(cudaGetLastError());
+    GW_LAUNCH_OK();
     GW_TRY(scan_exclusive_i64(is_light, light_before, n, n_light, s));
     GW_TRY(scan_exclusive_f64(ql, lsum, n, l_total, s));
     GW_TRY(scan_exclusive_f64(qh, hsum, n, h_total, s));
     alias_compact_kernel<<<blocks, 256, 0, s>>>(n, q, light_before, n_light, lsum, l_total, hsum,
                                                 light_id, LP, heavy_id, HP);
-    GW_CUDA_OK(cudaGetLastError());
+    GW_LAUNCH_OK();
     alias_assign_kernel<<<blocks, 256, 0, s>>>(n, q, light_before, n_light, heavy_id, LP, HP, table);
-    GW_CUDA_OK(cudaGetLastError());
+    GW_LAUNCH_OK();
     return GW_OK;
 }
 
@@ -525,7 +530,7 @@ extern "C" int gw_sgns_init(int32_t n, int32_t d, const int32_t *rank_of_node, c
     const int64_t total = (int64_t)n * d;
     sgns_init_kernel<<<(unsigned)ceil_div<int64_t>(total, 256), 256, 0, s>>>(n, d, rank_of_node,
                                                                             rng_rows, syn0, syn1neg);
-    GW_CUDA_OK(cudaGetLastError());
+    GW_LAUNCH_OK();
     return GW_OK;
 }
 

@@ -219,7 +219,7 @@ extern "C" int gw_mean_sem_f32(const float *sims, int64_t rows, int32_t nreps, f
     if (rows == 0) return GW_OK;
     GW_REQUIRE(sims && mean && sem, "gw_mean_sem_f32: null argument");
     mean_sem_kernel<<<(unsigned)ceil_div<int64_t>(rows, 128), 128, 0, s>>>(sims, rows, nreps, mean, sem);
-    GW_CUDA_OK(cudaGetLastError());
+    GW_LAUNCH_OK();
     return GW_OK;
 }
 
@@ -232,7 +232,7 @@ extern "C" int gw_cosine_pairs(int32_t d, const float *vectors, int64_t m, const
     if (m == 0) return GW_OK;
     GW_REQUIRE(vectors && a_idx && b_idx && sims, "gw_cosine_pairs: null argument");
     cosine_pairs_kernel<<<(unsigned)ceil_div<int64_t>(m, 256), 256, 0, s>>>(d, vectors, m, a_idx, b_idx, sims);
-    GW_CUDA_OK(cudaGetLastError());
+    GW_LAUNCH_OK();
     return GW_OK;
 }
 
@@ -258,13 +258,13 @@ extern "C" int gw_null_similarities(int32_t n, const int32_t *row_ptr, const int
     GW_CUDA_OK(t_norm.alloc(sizeof(float) * (size_t)n, s));
     GW_CUDA_OK(t_cnt.alloc(sizeof(int64_t), s));
     null_flags_kernel<<<num_sms() * 8, 256, 0, s>>>(n, row_ptr, col_idx, t_rows.as<int32_t>(), t_flag.as<int64_t>());
-    GW_CUDA_OK(cudaGetLastError());
+    GW_LAUNCH_OK();
     GW_TRY(scan_exclusive_i64(t_flag.as<int64_t>(), t_flag.as<int64_t>(), A, t_cnt.as<int64_t>(), s));
     row_norms_kernel<<<ceil_div(n, 256), 256, 0, s>>>(n, d, vectors, t_norm.as<float>());
-    GW_CUDA_OK(cudaGetLastError());
+    GW_LAUNCH_OK();
     null_sims_kernel<<<(unsigned)ceil_div<int64_t>(A, 256), 256, 0, s>>>(
         A, d, vectors, t_norm.as<float>(), t_rows.as<int32_t>(), col_idx, t_flag.as<int64_t>(), sims_out);
-    GW_CUDA_OK(cudaGetLastError());
+    GW_LAUNCH_OK();
     GW_CUDA_OK(cudaMemcpyAsync(count_out_host, t_cnt.ptr, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     GW_CUDA_OK(cudaStreamSynchronize(s));
     return GW_OK;
@@ -279,10 +279,10 @@ extern "C" int gw_sort_f32(float *keys, int64_t count, gw_stream_t stream)
     const unsigned blocks = (unsigned)ceil_div<int64_t>(count, 256);
     uint32_t *x = reinterpret_cast<uint32_t *>(keys);
     f32_to_sortable_kernel<<<blocks, 256, 0, s>>>(count, x);
-    GW_CUDA_OK(cudaGetLastError());
+    GW_LAUNCH_OK();
     GW_TRY(radix_sort_u32(x, nullptr, count, 32, s));
     sortable_to_f32_kernel<<<blocks, 256, 0, s>>>(count, x);
-    GW_CUDA_OK(cudaGetLastError());
+    GW_LAUNCH_OK();
     return GW_OK;
 }
 
@@ -295,7 +295,7 @@ extern "C" int gw_psim(const float *null_sorted, int64_t n_null, const float *si
     if (m == 0) return GW_OK;
     GW_REQUIRE(sims && pvals, "gw_psim: null argument");
     psim_kernel<<<(unsigned)ceil_div<int64_t>(m, 256), 256, 0, s>>>(null_sorted, n_null, sims, m, ranks, pvals);
-    GW_CUDA_OK(cudaGetLastError());
+    GW_LAUNCH_OK();
     return GW_OK;
 }
 
@@ -315,19 +315,19 @@ extern "C" int gw_bh_segmented(const double *pvals, int64_t m, const int64_t *se
     GW_CUDA_OK(t_raw.alloc(sizeof(SegVal) * (size_t)m, s));
     const unsigned blocks = (unsigned)ceil_div<int64_t>(m, 256);
     bh_keys_kernel<<<blocks, 256, 0, s>>>(m, pvals, t_keys.as<uint64_t>(), t_idx.as<uint32_t>());
-    GW_CUDA_OK(cudaGetLastError());
+    GW_LAUNCH_OK();
     GW_TRY(radix_sort_u64(t_keys.as<uint64_t>(), t_idx.as<uint32_t>(), m, 64, s));
     bh_segment_keys_kernel<<<blocks, 256, 0, s>>>(m, t_idx.as<uint32_t>(), seg_ptr, nseg, t_seg.as<uint32_t>());
-    GW_CUDA_OK(cudaGetLastError());
+    GW_LAUNCH_OK();
     int bits = 1;
     while (bits < 32 && ((int64_t)1 << bits) < nseg) ++bits;
     if (nseg > 1) GW_TRY(radix_sort_u32(t_seg.as<uint32_t>(), t_idx.as<uint32_t>(), m, bits, s));
     bh_raw_kernel<<<blocks, 256, 0, s>>>(m, pvals, t_idx.as<uint32_t>(), t_seg.as<uint32_t>(), seg_ptr,
                                          t_raw.as<SegVal>());
-    GW_CUDA_OK(cudaGetLastError());
+    GW_LAUNCH_OK();
     GW_TRY(scan_segmented_suffix_min(t_raw.as<SegVal>(), t_raw.as<SegVal>(), m, s));
     bh_store_kernel<<<blocks, 256, 0, s>>>(m, t_raw.as<SegVal>(), t_idx.as<uint32_t>(), qvals);
-    GW_CUDA_OK(cudaGetLastError());
+    GW_LAUNCH_OK();
     return GW_OK;
 }
 
@@ -340,6 +340,6 @@ extern "C" int gw_log_stats(const double *vals, int64_t rows, int32_t nreps, dou
     if (rows == 0) return GW_OK;
     GW_REQUIRE(vals && out, "gw_log_stats: null argument");
     log_stats_kernel<<<(unsigned)ceil_div<int64_t>(rows, 128), 128, 0, s>>>(vals, rows, nreps, out);
-    GW_CUDA_OK(cudaGetLastError());
+    GW_LAUNCH_OK();
     return GW_OK;
 }

@@ -34,10 +34,17 @@ walk_uniform_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restri
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < nslots; o += nthreads) {
         const int64_t p = slot_begin + o;
-        const int64_t it = p / A, r = p - it * A;
-        // (r * stride) % A with r, stride < A < 2^31: the product fits 64 bits
-        const int64_t e = (int64_t)(((uint64_t)r * stride) % (uint64_t)A);
-        const uint64_t w = (uint64_t)e * (uint64_t)niter + (uint64_t)it;
+        int64_t e;
+        uint64_t w;
+        if (stride == 0) {  // canonical (reference corpus) order: slot == walk id
+            w = (uint64_t)p;
+            e = p / niter;
+        } else {
+            const int64_t it = p / A, r = p - it * A;
+            // (r * stride) % A with r, stride < A < 2^31: the product fits 64 bits
+            e = (int64_t)(((uint64_t)r * stride) % (uint64_t)A);
+            w = (uint64_t)e * (uint64_t)niter + (uint64_t)it;
+        }
         int32_t v = __ldg(row_of_entry + e);
         __stcs(tokens + o, v);
         u32x4 rnd = {0, 0, 0, 0};
@@ -72,8 +79,8 @@ extern "C" int gw_walk_uniform(int32_t n, int64_t nnz, const int32_t *row_ptr,
     GW_REQUIRE(slot_begin >= 0 && slot_begin <= slot_end && slot_end <= W,
                "gw_walk_uniform: slots [%lld,%lld) outside [0,%lld)", (long long)slot_begin,
                (long long)slot_end, (long long)W);
-    GW_REQUIRE(stride >= 1 && stride < (uint64_t)A + (A == 1), "gw_walk_uniform: stride must be in [1, A)");
-    {
+    GW_REQUIRE(stride < (uint64_t)A + (A == 1), "gw_walk_uniform: stride must be in [0, A)");
+    if (stride != 0) {
         uint64_t a = (uint64_t)A, b = stride;
         while (b) { const uint64_t t = a % b; a = b; b = t; }
         GW_REQUIRE(a == 1, "gw_walk_uniform: stride %llu is not coprime to A=%lld",
@@ -85,7 +92,7 @@ extern "C" int gw_walk_uniform(int32_t n, int64_t nnz, const int32_t *row_ptr,
     GW_CUDA_OK(rows.alloc(sizeof(int32_t) * (size_t)A, s));
     const int sms = num_sms();
     expand_rows_kernel<<<sms * 8, 256, 0, s>>>(n, row_ptr, rows.as<int32_t>());
-    GW_CUDA_OK(cudaGetLastError());
+    GW_LAUNCH_OK();
     // grid: a multiple of the SM count, 8 resident CTAs of 256 threads per SM (2048 threads/SM)
     int64_t blocks = ceil_div<int64_t>(nslots, kWalkThreads);
     const int64_t cap = (int64_t)sms * 8 * 4;
@@ -93,6 +100,6 @@ extern "C" int gw_walk_uniform(int32_t n, int64_t nnz, const int32_t *row_ptr,
     walk_uniform_kernel<<<(unsigned)blocks, kWalkThreads, 0, s>>>(
         row_ptr, col_idx, rows.as<int32_t>(), A, niter, L, (uint32_t)seed, (uint32_t)(seed >> 32),
         stride, slot_begin, nslots, tokens);
-    GW_CUDA_OK(cudaGetLastError());
+    GW_LAUNCH_OK();
     return GW_OK;
 }

@@ -58,7 +58,7 @@ class WalkCorpus(Sequence):
         self.niter = int(niter)
         self.stride = int(stride)
         self.A = csr.nnz
-        self._inv = pow(self.stride, -1, self.A) if self.A > 1 else 0
+        self._inv = pow(self.stride, -1, self.A) if (self.A > 1 and self.stride > 0) else 0
 
     def __len__(self):
         return int(self.tokens.shape[1])
@@ -69,6 +69,8 @@ class WalkCorpus(Sequence):
 
     def slots_of(self, idx):
         idx = np.asarray(idx, dtype=np.int64)
+        if self.stride == 0:
+            return idx
         e, it = idx // self.niter, idx % self.niter
         r = (e * self._inv) % self.A if self.A > 1 else e
         return it * self.A + r
@@ -160,7 +162,8 @@ class DeepWalk(object):
 
         ``workers`` is accepted for API compatibility (the GPU runs one thread per walk).
         ``stride`` selects the storage-slot permutation (None: golden-ratio stride coprime to A,
-        which spreads the start nodes of concurrently trained walks; 1: plain iteration-major).
+        which spreads the start nodes of concurrently trained walks; 1: plain iteration-major;
+        0: the reference's node-major corpus order).
         """
         import torch
         _lib.require_cuda()
@@ -246,6 +249,37 @@ class DeepWalk(object):
             raise ValueError('min_count>1 is not implemented; GeneWalk uses min_count=1')
         logger.info('Generating node vectors...')
         start = time.time()
+        dv = self.train_device(vector_size=vector_size, negative=negative, epochs=epochs,
+                               alpha=alpha, min_alpha=min_alpha, init_seed=init_seed,
+                               ns_exponent=ns_exponent, batch_words=batch_words,
+                               max_threads=max_threads, sgns_seed=sgns_seed)
+        # results -> host (the only synchronisation of the replicate)
+        nodes = dv['nodes']
+        nv = int(dv['n_vocab'].item())
+        order = dv['node_of_rank'][:nv].long()
+        vectors = dv['syn0'].index_select(0, order).cpu().numpy()
+        out_layer = dv['syn1neg'].index_select(0, order).cpu().numpy()
+        cnt = dv['counts'].index_select(0, order).cpu().numpy()
+        order_h = order.cpu().numpy()
+        wv = NodeVectors([nodes[i] for i in order_h], vectors, counts=cnt)
+        wv.node_ids = order_h.astype(np.int32)   # row r of wv.vectors is graph node node_ids[r]
+        self.model = Word2VecModel(wv, syn1neg=out_layer, sg=1, vector_size=int(vector_size),
+                                   window=window, min_count=min_count, negative=negative,
+                                   sample=sample, epochs=epochs, alpha=alpha, min_alpha=min_alpha,
+                                   seed=init_seed, ns_exponent=ns_exponent,
+                                   corpus_count=dv['W'], workers=workers)
+        end = time.time()
+        self.timings['word2vec_s'] = end - start
+        logger.info('Generating node vectors done in %.2fs' % (end - start))
+
+    def train_device(self, vector_size=8, negative=5, epochs=5, alpha=0.025, min_alpha=0.0001,
+                     init_seed=1, ns_exponent=0.75, batch_words=10000, max_threads=0,
+                     sgns_seed=None, epoch_hook=None):
+        """Enqueue vocabulary, alias table, init and the SGNS epochs on the current stream and
+        return the device tensors (no host synchronisation).  ``epoch_hook(ep, when)`` is called
+        with when in {'before', 'after'} around every epoch's launch (bench.py records CUDA
+        events there)."""
+        import torch
         nodes, n, tokens = self._device_corpus()
         L, W = int(tokens.shape[0]), int(tokens.shape[1])
         d = int(vector_size)
@@ -271,29 +305,22 @@ class DeepWalk(object):
         _lib.call('gw_count_tokens', _lib.ptr(tokens), L * W, n, _lib.ptr(counts), st)
         _lib.call('gw_vocab_rank', n, _lib.ptr(counts), _lib.ptr(rank_of_node),
                   _lib.ptr(node_of_rank), _lib.ptr(n_vocab), st)
-        _lib.call('gw_alias_build', n, _lib.ptr(counts), ns_exponent, _lib.ptr(alias), st)
+        _lib.call('gw_alias_build', n, _lib.ptr(counts), float(ns_exponent), _lib.ptr(alias), st)
         _lib.call('gw_sgns_init', n, d, _lib.ptr(rank_of_node), _lib.ptr(rng_rows), _lib.ptr(syn0),
                   _lib.ptr(syn1neg), st)
-        job_walks = max(1, batch_words // max(L, 1))
-        _lib.call('gw_sgns_train', n, d, _lib.ptr(tokens), W, L, int(window), int(negative), epochs,
-                  0, epochs, alpha, min_alpha, job_walks, _lib.ptr(alias), _lib.ptr(syn0),
-                  _lib.ptr(syn1neg), int(sgns_seed), max_threads, st)
-        # results -> host (the only synchronisation of the replicate)
-        nv = int(n_vocab.item())
-        order = node_of_rank[:nv].long()
-        vectors = syn0.index_select(0, order).cpu().numpy()
-        out_layer = syn1neg.index_select(0, order).cpu().numpy()
-        cnt = counts.index_select(0, order).cpu().numpy()
-        order_h = order.cpu().numpy()
-        wv = NodeVectors([nodes[i] for i in order_h], vectors, counts=cnt)
-        wv.node_ids = order_h.astype(np.int32)   # row r of wv.vectors is graph node node_ids[r]
-        self.model = Word2VecModel(wv, syn1neg=out_layer, sg=1, vector_size=d, window=window,
-                                   min_count=min_count, negative=negative, sample=sample,
-                                   epochs=epochs, alpha=alpha, min_alpha=min_alpha, seed=init_seed,
-                                   ns_exponent=ns_exponent, corpus_count=W, workers=workers)
-        end = time.time()
-        self.timings['word2vec_s'] = end - start
-        logger.info('Generating node vectors done in %.2fs' % (end - start))
+        job_walks = max(1, int(batch_words) // max(L, 1))
+        for ep in range(int(epochs)):
+            if epoch_hook is not None:
+                epoch_hook(ep, 'before')
+            _lib.call('gw_sgns_train', n, d, _lib.ptr(tokens), W, L, 1, int(negative), int(epochs),
+                      ep, ep + 1, float(alpha), float(min_alpha), job_walks, _lib.ptr(alias),
+                      _lib.ptr(syn0), _lib.ptr(syn1neg), int(sgns_seed), int(max_threads), st)
+            if epoch_hook is not None:
+                epoch_hook(ep, 'after')
+        return {'nodes': nodes, 'n': n, 'W': W, 'L': L, 'syn0': syn0, 'syn1neg': syn1neg,
+                'counts': counts, 'rank_of_node': rank_of_node, 'node_of_rank': node_of_rank,
+                'n_vocab': n_vocab, 'alias': alias, 'rng_rows': rng_rows,
+                'h2d_bytes': rows.nbytes}
 
 
 # ---------------------------------------------------------------------------------------------

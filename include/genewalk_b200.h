@@ -47,6 +47,8 @@ typedef struct {
 
 int gw_version(void);
 const char *gw_last_error(void);
+/* number of kernels this library has launched since it was loaded (statistic for benchmarks) */
+long long gw_launch_count(void);
 /* number of CUDA devices visible, or a negative gw_status */
 int gw_device_count(void);
 
@@ -75,7 +77,8 @@ int gw_config_model(int32_t n, const int32_t *degrees, int64_t S, uint64_t seed,
  * run_single_walk (deepwalk.py:50-96,145-200).  W = niter*A walks; canonical walk id
  * w = e*niter + it is the walk's position in the reference's serial corpus (node-major).
  * Storage slot p holds walk (it = p / A, e = ((p % A) * stride) % A); stride must be coprime to A
- * (1 = plain iteration-major order).  Step s (1..L-1) of walk w consumes word (s-1)&3 of
+ * (1 = plain iteration-major order; 0 = slot p holds walk w = p, the reference's corpus order).
+ * Step s (1..L-1) of walk w consumes word (s-1)&3 of
  * Philox4x32-10(ctr {lo32(w), hi32(w), (s-1)>>2, 0x57}, key {lo32(seed), hi32(seed)}) and moves
  * to col_idx[row_ptr[v] + mulhi32(word, deg(v))].
  * Writes slots [slot_begin, slot_end) to tokens[i*(slot_end-slot_begin) + (p - slot_begin)].

@@ -72,7 +72,7 @@ void gwo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
  * Canonical walk id  w = e * niter + it   (e = adjacency entry, it = iteration) is the position
  * of the walk in the reference's serial corpus (deepwalk.py:67-70): node-major, niter*deg each.
  * Storage slot p -> (it = p / A, r = p % A, e = (r * stride) % A), stride coprime to A; stride 1
- * with it-major order is the plain interleaving.  tokens are position-major: tokens[i*W + p].
+ * with it-major order is the plain interleaving; stride 0 stores walk w in slot w (corpus order).  tokens are position-major: tokens[i*W + p].
  * Step s (1..L-1) of walk w consumes word (s-1)&3 of
  *   Philox(ctr = {lo32(w), hi32(w), (s-1)>>2, 0x57}, key = {lo32(seed), hi32(seed)})
  * and moves to col_idx[row_ptr[v] + mulhi32(word, deg(v))].
@@ -91,9 +91,16 @@ int gwo_walk_uniform(int32_t n, const int32_t *row_ptr, const int32_t *col_idx, 
         for (int32_t k = row_ptr[v]; k < row_ptr[v + 1]; ++k) src[k] = v;
     const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     for (int64_t p = slot_begin; p < slot_end; ++p) {
-        const int64_t it = p / A, r = p % A;
-        const int64_t e = (int64_t)(((unsigned __int128)(uint64_t)r * stride) % (uint64_t)A);
-        const uint64_t w = (uint64_t)e * (uint64_t)niter + (uint64_t)it;
+        int64_t e;
+        uint64_t w;
+        if (stride == 0) { /* canonical order: slot == walk id == position in the reference corpus */
+            w = (uint64_t)p;
+            e = p / niter;
+        } else {
+            const int64_t it = p / A, r = p % A;
+            e = (int64_t)(((unsigned __int128)(uint64_t)r * stride) % (uint64_t)A);
+            w = (uint64_t)e * (uint64_t)niter + (uint64_t)it;
+        }
         int32_t v = src[e];
         int64_t o = p - slot_begin;
         tokens_out[o] = v;

@@ -97,3 +97,15 @@ def log_stats(vals):
         g_std = eps
     return (g_mean, g_mean * (g_std ** (-1.96 / np.sqrt(nreps))),
             g_mean * (g_std ** (1.96 / np.sqrt(nreps))))
+
+
+def gene_padj(sims, srd_sorted, seg_ptr):
+    """Per-pair gene_padj of perform_statistics.py:100-187 from raw similarities:
+    sims [nreps, m] -> psim -> per-gene BH per replicate -> log_stats()[0] across replicates."""
+    sims = np.atleast_2d(np.asarray(sims, dtype=np.float32))
+    nreps, m = sims.shape
+    q = np.empty((nreps, m))
+    for r in range(nreps):
+        q[r] = fdrcorrection_segmented(psim(srd_sorted, sims[r]), seg_ptr)
+    eps = 1e-16
+    return np.exp(np.log(q + eps).mean(axis=0)) - eps

@@ -75,3 +75,100 @@ def csr_arrays(n, n_edges, seed, power_law=True, self_loops=0):
     row_ptr = np.zeros(n + 1, dtype=np.int64)
     np.add.at(row_ptr, src + 1, 1)
     return np.cumsum(row_ptr).astype(np.int32), dst
+
+
+def modular_gene_go_network(n_genes=2000, n_go=300, n_modules=40, n_gene_edges=12000,
+                            n_annot=7000, n_isa=1000, p_in=0.8, seed=1, dup_frac=0.1):
+    """C1-shaped network WITH planted structure, so that some gene-GO pairs are genuinely
+    significant: genes are split into modules; a fraction p_in of gene-gene edges stay inside a
+    module; every module owns a few GO terms that annotate its genes (fraction p_in of the
+    annotation edges), the rest of the annotations are Zipf noise.  Returns (graph, genes)."""
+    rng = np.random.default_rng(seed)
+    genes = ['G%05d' % i for i in range(n_genes)]
+    gos = ['GO:9%06d' % i for i in range(n_go)]
+    mg = nx.MultiGraph()
+    mg.add_nodes_from(genes)
+    for i, g in enumerate(gos):
+        mg.add_node(g, GO=g, name='term %d' % i, domain=DOMAINS[i % 3])
+    module = rng.integers(0, n_modules, size=n_genes)
+    members = [np.nonzero(module == k)[0] for k in range(n_modules)]
+    terms_of = [rng.choice(n_go, size=4, replace=False) for _ in range(n_modules)]
+    a = rng.integers(0, n_genes, size=n_gene_edges)
+    inside = rng.random(n_gene_edges) < p_in
+    b = np.where(inside, [rng.choice(members[module[x]]) for x in a],
+                 rng.integers(0, n_genes, size=n_gene_edges))
+    keep = a != b
+    a, b = a[keep], b[keep]
+    mg.add_edges_from(((genes[x], genes[y], {'label': 'interacts'}) for x, y in zip(a, b)))
+    ndup = int(len(a) * dup_frac)
+    mg.add_edges_from(((genes[x], genes[y], {'label': 'regulates'})
+                       for x, y in zip(a[:ndup], b[:ndup])))
+    ga = rng.integers(0, n_genes, size=n_annot)
+    tw = (np.arange(1, n_go + 1, dtype=np.float64)) ** -1.2
+    tw /= tw.sum()
+    own = rng.random(n_annot) < p_in
+    gt = np.where(own, [rng.choice(terms_of[module[x]]) for x in ga],
+                  rng.choice(n_go, size=n_annot, p=tw))
+    mg.add_edges_from(((genes[x], gos[y], {'label': 'GO:annotation'}) for x, y in zip(ga, gt)))
+    child = rng.integers(1, n_go, size=n_isa)
+    parent = (rng.random(n_isa) * child).astype(np.int64)
+    mg.add_edges_from(((gos[c], gos[p], {'label': 'GO:is_a'}) for c, p in zip(child, parent)))
+    return mg, [{'ID': g} for g in genes]
+
+
+def human_scale_edges(seed=2, n_genes=20000, n_go=18000, n_gene_edges=700000, n_annot=250000,
+                      n_isa=50000, n_modules=500, p_in=0.5):
+    """C2/C3 (BASELINE.json configs[1..2]): ~20k genes + ~18k GO terms, ~1M edges.
+    Gene-gene edges follow a Chung-Lu model with power-law weights (exponent 2.5) mixed with
+    planted modules; gene-GO annotations are half module-specific, half Zipf; GO-GO edges form a
+    DAG (child -> parent with smaller index).  Returns (n, u, v, is_go_node) as numpy arrays with
+    genes first (ids 0..n_genes-1) and GO terms after."""
+    rng = np.random.default_rng(seed)
+    w = (np.arange(1, n_genes + 1, dtype=np.float64) + 10.0) ** (-1.0 / 1.5)
+    w /= w.sum()
+    a = rng.choice(n_genes, size=n_gene_edges, p=w)
+    module = rng.integers(0, n_modules, size=n_genes)
+    order = np.argsort(module, kind='stable')
+    start = np.searchsorted(module[order], np.arange(n_modules))
+    size = np.bincount(module, minlength=n_modules)
+    inside = rng.random(n_gene_edges) < p_in
+    pick = start[module[a]] + (rng.random(n_gene_edges) * size[module[a]]).astype(np.int64)
+    b = np.where(inside, order[pick], rng.choice(n_genes, size=n_gene_edges, p=w))
+    keep = a != b
+    a, b = a[keep], b[keep]
+    terms_of = rng.integers(0, n_go, size=(n_modules, 6))
+    ga = rng.choice(n_genes, size=n_annot, p=w)
+    tw = (np.arange(1, n_go + 1, dtype=np.float64)) ** -1.0
+    tw /= tw.sum()
+    own = rng.random(n_annot) < 0.5
+    gt = np.where(own, terms_of[module[ga], rng.integers(0, 6, size=n_annot)],
+                  rng.choice(n_go, size=n_annot, p=tw))
+    child = rng.integers(1, n_go, size=n_isa)
+    parent = (rng.random(n_isa) * child).astype(np.int64)
+    u = np.concatenate([a, ga, n_genes + child]).astype(np.int32)
+    v = np.concatenate([b, n_genes + gt, n_genes + parent]).astype(np.int32)
+    n = n_genes + n_go
+    is_go = np.arange(n) >= n_genes
+    return n, u, v, is_go
+
+
+def edges_to_networkx(n, u, v, is_go, n_genes):
+    """The nx.MultiGraph a GeneWalk assembler would hand to the hot path (string ids, GO attrs)."""
+    names = ['G%05d' % i for i in range(n_genes)] + ['GO:9%06d' % i for i in range(n - n_genes)]
+    mg = nx.MultiGraph()
+    mg.add_nodes_from(names[:n_genes])
+    for i in range(n_genes, n):
+        mg.add_node(names[i], GO=names[i], name='term %d' % (i - n_genes),
+                    domain=DOMAINS[i % 3])
+    mg.add_edges_from(zip([names[x] for x in u.tolist()], [names[x] for x in v.tolist()]))
+    return mg, [{'ID': g} for g in names[:n_genes]]
+
+
+def csr_from_edges_numpy(n, u, v):
+    """Distinct-neighbour CSR (rows sorted by neighbour id) of an undirected multi-edge list."""
+    key = np.unique(np.concatenate([u.astype(np.int64) * n + v, v.astype(np.int64) * n + u]))
+    src = (key // n).astype(np.int32)
+    dst = (key % n).astype(np.int32)
+    row_ptr = np.zeros(n + 1, dtype=np.int64)
+    np.add.at(row_ptr, src + 1, 1)
+    return np.cumsum(row_ptr).astype(np.int32), dst

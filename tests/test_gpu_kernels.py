@@ -15,9 +15,21 @@ from oracle import config_model_ref, stats_ref  # noqa: E402
 from tests import graphs  # noqa: E402
 
 
+_KEEP = []   # device tensors whose raw pointers were handed to the library stay alive per test
+
+
 def dev(a, dtype=None):
     a = np.ascontiguousarray(a, dtype=dtype)
-    return torch.from_numpy(a).cuda()
+    t = torch.from_numpy(a).cuda()
+    _KEEP.append(t)
+    return t
+
+
+@pytest.fixture(autouse=True)
+def _release_device_tensors():
+    yield
+    torch.cuda.synchronize()
+    del _KEEP[:]
 
 
 def st():
@@ -42,6 +54,7 @@ def gpu_walks(row_ptr, col_idx, niter, L, seed, stride=1, begin=0, end=None):
 
 @pytest.mark.parametrize('n,m,niter,L,stride', [(50, 200, 7, 10, 1), (300, 2000, 5, 10, None),
                                                 (1000, 5000, 3, 13, None), (10, 12, 100, 2, 1),
+                                                (200, 900, 6, 10, 0),
                                                 (64, 300, 4, 1, 1)])
 def test_walks_bit_exact(n, m, niter, L, stride):
     from genewalk_b200.csr import coprime_stride
@@ -213,8 +226,11 @@ def test_alias_table_reproduces_distribution(n):
     implied = olib.alias_implied_distribution(prob, alias)
     w = np.where(counts > 0, counts.astype(np.float64) ** 0.75, 0.0)
     target = w / w.sum()
-    # float32 prob storage: each slot's split is exact to 2^-24 of a slot (1/n)
-    assert np.abs(implied - target).max() <= 2.0 ** -23 / n + 1e-15
+    # float32 prob storage: each slot's split is exact to 2^-24 of a slot (1/n); an item collects
+    # one such rounding from its own slot and from every slot aliased to it
+    refs = 1 + np.bincount(alias, minlength=n)
+    assert (np.abs(implied - target) <= refs * (2.0 ** -24 / n) + 1e-15).all()
+    assert abs(implied.sum() - 1.0) < 1e-9
     assert implied[counts == 0].max(initial=0.0) == 0.0      # absent nodes are never drawn
 
 
@@ -284,14 +300,15 @@ def test_sgns_unsupported_raises():
 
 
 def test_sgns_hogwild_close_to_sequential():
-    """Full-width Hogwild run vs the sequential oracle on the same corpus/negatives: rows differ by
-    reordering of float adds and stale reads only; cosine between the two solutions stays high."""
+    """Hogwild run (64 walks in flight on a 200-node graph) vs the sequential oracle on the same
+    corpus/negatives: rows differ by reordering of float adds and stale reads only; the similarity
+    structure of the two solutions agrees."""
     n, d, K, epochs = 200, 8, 5, 5
     tok, prob, alias, syn0, syn1 = sgns_case(n, 1500, 20, 10, d, K, epochs, seed=21)
     want0, want1 = syn0.copy(), syn1.copy()
     olib.sgns_train(tok, n, d, want0, want1, sampler=1, K=K, epochs=epochs, alias_prob=prob,
                     alias_idx=alias, seed=77)
-    got0, _ = gpu_sgns(tok, n, d, K, epochs, prob, alias, syn0, syn1, 77, max_threads=0)
+    got0, _ = gpu_sgns(tok, n, d, K, epochs, prob, alias, syn0, syn1, 77, max_threads=64)
     assert np.isfinite(got0).all()
     # pairwise cosine structure agrees: compare similarity of neighbours
     row_ptr, col_idx = graphs.csr_arrays(n, 1500, seed=21, self_loops=2)
