@@ -116,7 +116,7 @@ def run_reference(args):
     graphs, n, u, v, is_go, ng = build_inputs(args.scale)
     row_ptr, col_idx = graphs.csr_from_edges_numpy(n, u, v)
     from oracle import lib as olib
-    threads = olib.lib().gwo_max_threads()
+    threads = olib.lib().gwo_lanes()
     vals, sample = [], ''
     t_all = time.perf_counter()
     for i in range(args.warmup + args.steps):
@@ -202,7 +202,7 @@ def run_ours(args):
         w0.record()
         dw.get_walks()
         w1.record()
-        dv = dw.train_device(vector_size=D, negative=K, epochs=EPOCHS, max_threads=args.max_threads,
+        dv = dw.train_device(vector_size=D, negative=K, epochs=EPOCHS, lanes=args.lanes,
                              epoch_hook=hook if timed else None)
         # the replicate's product in the pipeline: gene-GO similarities (fixed length), exchanged
         sims = torch.empty(m_pairs, dtype=torch.float32, device='cuda')
@@ -262,12 +262,12 @@ def run_ours(args):
     h2d = csr.row_ptr.nbytes + csr.col_idx.nbytes + n * D * 4
     d2h = 0
     for i in range(min(args.warmup, 1)):
-        run_walks(mg, vector_size=D, walk_seed=7 + i, max_threads=args.max_threads)
+        run_walks(mg, vector_size=D, walk_seed=7 + i, lanes=args.lanes)
     barrier()
     e0 = time.perf_counter()
     for i in range(args.steps):
         dw = run_walks(mg, vector_size=D, walk_seed=100 + i * world + rank,
-                       max_threads=args.max_threads)
+                       lanes=args.lanes)
         wv = dw.model.wv
         d2h = wv.vectors.nbytes + dw.model.syn1neg.nbytes + wv.counts.nbytes + wv.node_ids.nbytes
         del dw
@@ -299,11 +299,11 @@ def run_ours(args):
                 'walk': {'steps_per_s': W * (WL - 1) / (walk_ms / 1e3), 'ms': walk_ms,
                          'achieved_gbs': BYTES_PER_STEP * W * (WL - 1) / (walk_ms / 1e3) / 1e9},
                 'sgns_kernel_pairs_per_s': pairs_launch / (k_avg / 1e3),
-                'max_threads': args.max_threads}
+                'lanes': args.lanes}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import lib as olib
         csr.to_host()
-        threads = olib.lib().gwo_max_threads()
+        threads = olib.lib().gwo_lanes()
         rate, sample = cpu_sample_rate(csr.row_ptr, csr.col_idx, threads)
         line['cpu_baseline'] = {'value': rate, 'unit': 'pairs/s', 'cores': threads, 'kind': 'port',
                                 'sample': sample}
@@ -320,7 +320,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--scale', type=float, default=1.0, help='shrink the workload (tests only)')
-    ap.add_argument('--max-threads', type=int, default=0, dest='max_threads')
+    ap.add_argument('--lanes', type=int, default=0, dest='lanes')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours' and args.scale == 1.0:

@@ -5,7 +5,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 SO_PATH = os.path.join(HERE, 'libgenewalk_b200.so')
-SOURCES = ['gw_scan_sort.cu', 'gw_walk.cu', 'gw_sgns.cu', 'gw_graph.cu', 'gw_stats.cu']
+SOURCES = ['gw_scan_sort.cu', 'gw_walk.cu', 'gw_sgns.cu', 'gw_sgns_train.cu', 'gw_graph.cu', 'gw_stats.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-fmad=false',  # every fp op rounds on its own: bit-exact against the oracle
               '-Xcompiler', '-fPIC', '--shared',

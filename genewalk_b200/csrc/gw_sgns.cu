@@ -1,4 +1,5 @@
-// gw_sgns.cu -- skip-gram negative sampling on L2-resident embedding tables.
+// gw_sgns.cu -- vocabulary, noise (alias) table and weight init of the SGNS trainer; the training
+// kernel itself is in gw_sgns_train.cu.
 // Replaces gensim.models.Word2Vec(sg=1, window=1, negative=K, sample=0) as called at
 // /root/reference/genewalk/deepwalk.py:135-139 (gensim itself is third-party and absent from the
 // reference tree; the update rule below is its published w2v_fast_sentence_sg_neg).
@@ -233,200 +234,6 @@ __global__ void sgns_init_kernel(int32_t n, int32_t d, const int32_t *__restrict
     }
 }
 
-// =============================================================================================
-// training
-// =============================================================================================
-constexpr int kExpTableSize = 1000;
-constexpr float kMaxExp = 6.0f;
-constexpr int kTrainThreads = 256;
-
-struct TrainParams {
-    const int32_t *tokens;
-    int64_t W;
-    int32_t L;
-    int32_t n;
-    int32_t K;
-    int32_t epochs;
-    int32_t epoch;
-    double alpha0;
-    double alpha_span;  // alpha0 - alpha_min
-    double alpha_min;
-    int64_t job_walks;
-    const gw_alias_entry *alias;
-    const float *exp_table;  // [1000] device copy of gensim's EXP_TABLE
-    float *syn0;
-    float *syn1neg;
-    uint32_t key0, key1;
-};
-
-__device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, float d)
-{
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c),
-                 "f"(d)
-                 : "memory");
-}
-
-template <int D> __device__ __forceinline__ void load_row(const float *p, float (&r)[D])
-{
-#pragma unroll
-    for (int k = 0; k < D; k += 4) {
-        const float4 v = __ldcg(reinterpret_cast<const float4 *>(p + k));  // L2, never stale L1
-        r[k] = v.x; r[k + 1] = v.y; r[k + 2] = v.z; r[k + 3] = v.w;
-    }
-}
-
-// sequential-order, unfused dot product: identical rounding to the CPU oracle used by the tests
-template <int D> __device__ __forceinline__ float dot_row(const float (&a)[D], const float (&b)[D])
-{
-    float f = 0.0f;
-#pragma unroll
-    for (int k = 0; k < D; ++k) f = __fadd_rn(f, __fmul_rn(a[k], b[k]));
-    return f;
-}
-
-__device__ __forceinline__ int32_t draw_negative(const TrainParams &P, uint32_t x0, uint32_t x1)
-{
-    const int32_t slot = (int32_t)__umulhi(x0, (uint32_t)P.n);
-    const float u = (float)(x1 >> 8) * (1.0f / 16777216.0f);
-    // the alias table is read-only for the whole kernel: non-coherent path, L1-cacheable
-    const int2 e = __ldg(reinterpret_cast<const int2 *>(P.alias) + slot);
-    return u < __int_as_float(e.x) ? slot : e.y;
-}
-
-// one (centre, context) pair; KT > 0: K known at compile time, all K+1 target rows are loaded
-// before the first use (memory-level parallelism); KT == 0: runtime K, one target at a time.
-template <int D, int KT>
-__device__ __forceinline__ void pair_update(const TrainParams &P, const float *s_exp,
-                                            int32_t centre, int32_t context, float alpha,
-                                            uint32_t p_lo, uint32_t p_hi, uint32_t q)
-{
-    float *row1_ptr = P.syn0 + (int64_t)context * D;
-    float row1[D], work[D];
-    load_row<D>(row1_ptr, row1);
-#pragma unroll
-    for (int k = 0; k < D; ++k) work[k] = 0.0f;
-    const uint32_t ctr2 = q << 4, ctr3 = ((uint32_t)P.epoch << 8) | kStreamSgns;
-
-    auto apply = [&](int32_t target, float label, const float (&row2)[D]) {
-        const float f = dot_row<D>(row1, row2);
-        if (f <= -kMaxExp || f >= kMaxExp) return;
-        const int idx = (int)((double)__fadd_rn(f, kMaxExp) * ((double)kExpTableSize / 6.0 / 2.0));
-        const float g = __fmul_rn(__fsub_rn(label, s_exp[idx]), alpha);
-#pragma unroll
-        for (int k = 0; k < D; ++k) work[k] = __fadd_rn(work[k], __fmul_rn(g, row2[k]));
-        float *row2_ptr = P.syn1neg + (int64_t)target * D;
-#pragma unroll
-        for (int k = 0; k < D; k += 4)
-            red_add_v4(row2_ptr + k, __fmul_rn(g, row1[k]), __fmul_rn(g, row1[k + 1]),
-                       __fmul_rn(g, row1[k + 2]), __fmul_rn(g, row1[k + 3]));
-    };
-
-    if constexpr (KT > 0) {
-        int32_t target[KT + 1];
-        target[0] = centre;
-        u32x4 r = {0, 0, 0, 0};
-#pragma unroll
-        for (int t = 1; t <= KT; ++t) {
-            const int w = 2 * (t - 1);
-            if ((w & 3) == 0) r = philox4x32_10(p_lo, p_hi, ctr2 | (uint32_t)(w >> 2), ctr3, P.key0, P.key1);
-            target[t] = (w & 3) == 0 ? draw_negative(P, r.x, r.y) : draw_negative(P, r.z, r.w);
-        }
-        float rows[KT + 1][D];
-#pragma unroll
-        for (int t = 0; t <= KT; ++t) load_row<D>(P.syn1neg + (int64_t)target[t] * D, rows[t]);
-#pragma unroll
-        for (int t = 0; t <= KT; ++t) {
-            if (t > 0 && target[t] == centre) continue;
-            if (t > 0) {
-                // an earlier target of THIS pair may be the same row: its update must be visible
-                // (the sequential oracle re-reads the row); reload only in that rare case
-                bool dup = false;
-#pragma unroll
-                for (int t2 = 0; t2 < t; ++t2) dup |= (target[t2] == target[t]);
-                if (dup) load_row<D>(P.syn1neg + (int64_t)target[t] * D, rows[t]);
-            }
-            apply(target[t], t == 0 ? 1.0f : 0.0f, rows[t]);
-        }
-    } else {
-        u32x4 r = {0, 0, 0, 0};
-        for (int t = 0; t <= P.K; ++t) {
-            int32_t target = centre;
-            if (t > 0) {
-                const int w = 2 * (t - 1);
-                if ((w & 3) == 0) r = philox4x32_10(p_lo, p_hi, ctr2 | (uint32_t)(w >> 2), ctr3, P.key0, P.key1);
-                target = (w & 3) == 0 ? draw_negative(P, r.x, r.y) : draw_negative(P, r.z, r.w);
-                if (target == centre) continue;
-            }
-            float row2[D];
-            load_row<D>(P.syn1neg + (int64_t)target * D, row2);
-            apply(target, t == 0 ? 1.0f : 0.0f, row2);
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < D; k += 4) red_add_v4(row1_ptr + k, work[k], work[k + 1], work[k + 2], work[k + 3]);
-}
-
-template <int D, int KT>
-__global__ void __launch_bounds__(kTrainThreads)
-sgns_train_kernel(const TrainParams P)
-{
-    __shared__ float s_exp[kExpTableSize];
-    for (int i = threadIdx.x; i < kExpTableSize; i += blockDim.x) s_exp[i] = P.exp_table[i];
-    __syncthreads();
-    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P.W; p += nthreads) {
-        // gensim _get_next_alpha at pushed = job*job_walks examples (fp64, unfused, as the oracle)
-        const int64_t pushed = (p / P.job_walks) * P.job_walks;
-        const double epoch_progress = __ddiv_rn((double)pushed, (double)P.W);
-        const double progress = __ddiv_rn(__dadd_rn((double)P.epoch, epoch_progress), (double)P.epochs);
-        double next_alpha = __dsub_rn(P.alpha0, __dmul_rn(P.alpha_span, progress));
-        if (next_alpha < P.alpha_min) next_alpha = P.alpha_min;
-        const float alpha = (float)next_alpha;
-        const uint32_t p_lo = (uint32_t)(uint64_t)p, p_hi = (uint32_t)((uint64_t)p >> 32);
-        int32_t prev = -1, cur = __ldcs(P.tokens + p);
-        for (int32_t i = 0; i < P.L && cur >= 0; ++i) {
-            const int32_t next = (i + 1 < P.L) ? __ldcs(P.tokens + (int64_t)(i + 1) * P.W + p) : -1;
-            if (prev >= 0) pair_update<D, KT>(P, s_exp, cur, prev, alpha, p_lo, p_hi, 2u * i);
-            if (next >= 0) pair_update<D, KT>(P, s_exp, cur, next, alpha, p_lo, p_hi, 2u * i + 1u);
-            prev = cur;
-            cur = next;
-        }
-    }
-}
-
-// gensim word2vec_inner.pyx init(): EXP_TABLE[i] = e/(e+1), e = exp((i/1000*2-1)*6) in REAL_t
-static void host_exp_table(float *t)
-{
-    for (int i = 0; i < kExpTableSize; ++i) {
-        const float x = ((float)i / (float)kExpTableSize * 2.0f - 1.0f) * 6.0f;
-        const float e = (float)exp((double)x);
-        t[i] = e / (e + 1.0f);
-    }
-}
-
-template <int D, int KT>
-static int launch_train(const TrainParams &P, int64_t max_threads, cudaStream_t s)
-{
-    int per_sm = 0;
-    GW_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sgns_train_kernel<D, KT>,
-                                                             kTrainThreads, 0));
-    if (per_sm < 1) per_sm = 1;
-    const int sms = num_sms();
-    int64_t threads = (int64_t)sms * per_sm * kTrainThreads;  // one resident wave, persistent
-    if (max_threads > 0 && max_threads < threads) threads = max_threads;
-    if (threads > P.W) threads = P.W;
-    // `threads` walks are in flight at any time (the Hogwild staleness knob).  Below one full
-    // CTA per SM the walks are spread over all SMs in 64-thread CTAs so that every SM's LSU/L1
-    // path carries part of the gather/reduction traffic.
-    int block = kTrainThreads;
-    if (threads < (int64_t)sms * kTrainThreads) block = 64;
-    if (threads < block) block = (int)threads;
-    const int64_t grid = ceil_div<int64_t>(threads, block);
-    sgns_train_kernel<D, KT><<<(unsigned)grid, block, 0, s>>>(P);
-    GW_LAUNCH_OK();
-    return GW_OK;
-}
-
 }  // namespace gw
 
 // =============================================================================================
@@ -531,52 +338,5 @@ extern "C" int gw_sgns_init(int32_t n, int32_t d, const int32_t *rank_of_node, c
     sgns_init_kernel<<<(unsigned)ceil_div<int64_t>(total, 256), 256, 0, s>>>(n, d, rank_of_node,
                                                                             rng_rows, syn0, syn1neg);
     GW_LAUNCH_OK();
-    return GW_OK;
-}
-
-extern "C" int gw_sgns_train(int32_t n, int32_t d, const int32_t *tokens, int64_t W, int32_t L,
-                             int32_t window, int32_t K, int32_t epochs, int32_t epoch_begin,
-                             int32_t epoch_end, double alpha0, double alpha_min, int64_t job_walks,
-                             const gw_alias_entry *alias_table, float *syn0, float *syn1neg,
-                             uint64_t seed, int64_t max_threads, gw_stream_t stream)
-{
-    using namespace gw;
-    cudaStream_t s = (cudaStream_t)stream;
-    GW_REQUIRE(n > 0 && tokens && alias_table && syn0 && syn1neg, "gw_sgns_train: null argument");
-    GW_REQUIRE(W > 0 && L >= 1 && L <= 4096, "gw_sgns_train: W=%lld L=%d out of range", (long long)W, L);
-    GW_REQUIRE(K >= 0 && K <= 32, "gw_sgns_train: negative=%d out of range [0,32]", K);
-    GW_REQUIRE(epochs >= 1 && epochs <= 65535 && epoch_begin >= 0 && epoch_begin <= epoch_end &&
-                   epoch_end <= epochs,
-               "gw_sgns_train: epochs=%d [%d,%d) invalid", epochs, epoch_begin, epoch_end);
-    GW_REQUIRE(job_walks >= 1 && max_threads >= 0, "gw_sgns_train: job_walks/max_threads invalid");
-    if (window != 1) {
-        set_error("gw_sgns_train: window=%d is not implemented (GeneWalk uses window=1)", window);
-        return GW_ERR_UNSUPPORTED;
-    }
-    if (d != 8 && d != 16 && d != 32) {
-        set_error("gw_sgns_train: vector_size=%d is not implemented (8, 16, 32)", d);
-        return GW_ERR_UNSUPPORTED;
-    }
-    GW_REQUIRE((reinterpret_cast<uintptr_t>(syn0) & 15) == 0 && (reinterpret_cast<uintptr_t>(syn1neg) & 15) == 0,
-               "gw_sgns_train: tables must be 16-byte aligned");
-    float h_exp[kExpTableSize];
-    host_exp_table(h_exp);
-    Temp d_exp;
-    GW_CUDA_OK(d_exp.alloc(sizeof h_exp, s));
-    // pageable source: the copy is staged before the call returns, so the stack buffer is safe
-    GW_CUDA_OK(cudaMemcpyAsync(d_exp.ptr, h_exp, sizeof h_exp, cudaMemcpyHostToDevice, s));
-    TrainParams P;
-    P.tokens = tokens; P.W = W; P.L = L; P.n = n; P.K = K; P.epochs = epochs; P.epoch = 0;
-    P.alpha0 = alpha0; P.alpha_span = alpha0 - alpha_min; P.alpha_min = alpha_min;
-    P.job_walks = job_walks; P.alias = alias_table; P.exp_table = d_exp.as<float>();
-    P.syn0 = syn0; P.syn1neg = syn1neg; P.key0 = (uint32_t)seed; P.key1 = (uint32_t)(seed >> 32);
-    for (int ep = epoch_begin; ep < epoch_end; ++ep) {
-        P.epoch = ep;
-        int rc;
-        if (d == 8) rc = (K == 5) ? launch_train<8, 5>(P, max_threads, s) : launch_train<8, 0>(P, max_threads, s);
-        else if (d == 16) rc = (K == 5) ? launch_train<16, 5>(P, max_threads, s) : launch_train<16, 0>(P, max_threads, s);
-        else rc = launch_train<32, 0>(P, max_threads, s);
-        GW_TRY(rc);
-    }
     return GW_OK;
 }

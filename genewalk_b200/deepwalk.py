@@ -161,9 +161,9 @@ class DeepWalk(object):
         """Generates walks (sentences) sampled by an (unbiased) random walk over the graph.
 
         ``workers`` is accepted for API compatibility (the GPU runs one thread per walk).
-        ``stride`` selects the storage-slot permutation (None: golden-ratio stride coprime to A,
-        which spreads the start nodes of concurrently trained walks; 1: plain iteration-major;
-        0: the reference's node-major corpus order).
+        ``stride`` selects the storage order (0, default: the reference's node-major corpus order,
+        which is also the order the learning-rate schedule of ``word2vec`` refers to; s > 0:
+        iteration-major with adjacency entries permuted by a stride coprime to A).
         """
         import torch
         _lib.require_cuda()
@@ -179,7 +179,7 @@ class DeepWalk(object):
             self.walks = []
             return
         W = int(self.niter) * A
-        stride = coprime_stride(A) if stride is None else int(stride)
+        stride = 0 if stride is None else int(stride)
         tokens = torch.empty((int(self.wl), W), dtype=torch.int32, device=csr.d_row_ptr.device)
         _lib.call('gw_walk_uniform', csr.n, A, _lib.ptr(csr.d_row_ptr), _lib.ptr(csr.d_col_idx),
                   int(self.niter), int(self.wl), self._walk_seed, stride, 0, W, _lib.ptr(tokens),
@@ -221,8 +221,11 @@ class DeepWalk(object):
         Same signature and defaults as the reference (deepwalk.py:98-99); the remaining gensim
         defaults can be overridden by keyword: ``epochs`` (5), ``alpha`` (0.025), ``min_alpha``
         (0.0001), ``seed`` (1, weight init), ``ns_exponent`` (0.75), ``batch_words`` (10000),
-        ``hs`` (0).  GPU-only knobs: ``max_threads`` (0 = one resident wave; the number of walks
-        trained concurrently under Hogwild) and ``sgns_seed`` (Philox key of the negative draws).
+        ``hs`` (0).  GPU-only knobs: ``lanes`` (number of concurrent workers, the analogue of
+        gensim's ``workers``: each trains one 1000-walk job at a time, taken from a queue in corpus
+        order; 0 = library default, 1 = sequential), ``chunk_walks`` (walks a worker takes from
+        the queue at a time; must divide the job size; 0 = library default) and ``sgns_seed``
+        (Philox key of the negative draws).
         """
         import torch
         _lib.require_cuda()
@@ -233,7 +236,8 @@ class DeepWalk(object):
         ns_exponent = float(kwargs.pop('ns_exponent', 0.75))
         batch_words = int(kwargs.pop('batch_words', 10000))
         hs = int(kwargs.pop('hs', 0))
-        max_threads = int(kwargs.pop('max_threads', 0))
+        lanes = int(kwargs.pop('lanes', 0))
+        chunk_walks = int(kwargs.pop('chunk_walks', 0))
         sgns_seed = kwargs.pop('sgns_seed', None)
         if kwargs:
             raise TypeError('word2vec() got unexpected keyword arguments %s' % sorted(kwargs))
@@ -252,7 +256,7 @@ class DeepWalk(object):
         dv = self.train_device(vector_size=vector_size, negative=negative, epochs=epochs,
                                alpha=alpha, min_alpha=min_alpha, init_seed=init_seed,
                                ns_exponent=ns_exponent, batch_words=batch_words,
-                               max_threads=max_threads, sgns_seed=sgns_seed)
+                               lanes=lanes, chunk_walks=chunk_walks, sgns_seed=sgns_seed)
         # results -> host (the only synchronisation of the replicate)
         nodes = dv['nodes']
         nv = int(dv['n_vocab'].item())
@@ -273,7 +277,7 @@ class DeepWalk(object):
         logger.info('Generating node vectors done in %.2fs' % (end - start))
 
     def train_device(self, vector_size=8, negative=5, epochs=5, alpha=0.025, min_alpha=0.0001,
-                     init_seed=1, ns_exponent=0.75, batch_words=10000, max_threads=0,
+                     init_seed=1, ns_exponent=0.75, batch_words=10000, lanes=0, chunk_walks=0,
                      sgns_seed=None, epoch_hook=None):
         """Enqueue vocabulary, alias table, init and the SGNS epochs on the current stream and
         return the device tensors (no host synchronisation).  ``epoch_hook(ep, when)`` is called
@@ -313,8 +317,9 @@ class DeepWalk(object):
             if epoch_hook is not None:
                 epoch_hook(ep, 'before')
             _lib.call('gw_sgns_train', n, d, _lib.ptr(tokens), W, L, 1, int(negative), int(epochs),
-                      ep, ep + 1, float(alpha), float(min_alpha), job_walks, _lib.ptr(alias),
-                      _lib.ptr(syn0), _lib.ptr(syn1neg), int(sgns_seed), int(max_threads), st)
+                      ep, ep + 1, float(alpha), float(min_alpha), job_walks, int(chunk_walks),
+                      _lib.ptr(alias),
+                      _lib.ptr(syn0), _lib.ptr(syn1neg), int(sgns_seed), int(lanes), st)
             if epoch_hook is not None:
                 epoch_hook(ep, 'after')
         return {'nodes': nodes, 'n': n, 'W': W, 'L': L, 'syn0': syn0, 'syn1neg': syn1neg,

@@ -113,22 +113,33 @@ int gw_alias_build(int32_t n, const int64_t *counts, double power, gw_alias_entr
 int gw_sgns_init(int32_t n, int32_t d, const int32_t *rank_of_node, const float *rng_rows,
                  float *syn0, float *syn1neg, gw_stream_t stream);
 
-/* Trains epochs [epoch_begin, epoch_end) of `epochs` over the W stored walks (window 1).
- * alpha of slot p in epoch ep = max(alpha_min, alpha0 - (alpha0-alpha_min) *
- * ((ep + floor(p/job_walks)*job_walks / W) / epochs)) (gensim _get_next_alpha, jobs of job_walks
- * walks).  Pair q = 2i + (j>i) of slot p draws its K negatives from Philox4x32-10(ctr {lo32(p),
- * hi32(p), (q<<4)|c, (ep<<8)|0x53}, key = seed): negative t uses words 2(t-1), 2(t-1)+1:
+/* Trains epochs [epoch_begin, epoch_end) of `epochs` over the W stored walks (window 1), stored in
+ * the corpus order the learning-rate schedule refers to (for GeneWalk: the reference's node-major
+ * order, gw_walk_uniform with stride 0).
+ * Parallel structure = gensim's: the corpus is cut into jobs of job_walks consecutive walks
+ * (gensim batch_words=10000 -> 1000 walks of 10); every walk of job j of epoch ep is trained with
+ * alpha = max(alpha_min, alpha0 - (alpha0-alpha_min) * ((ep + j*job_walks/W) / epochs))
+ * (gensim _get_next_alpha).  `lanes` workers (a worker = one group of d/2 <= 32 GPU threads; the
+ * analogue of gensim's `workers`) take chunks of chunk_walks consecutive walks (chunk_walks divides
+ * job_walks) from a queue in corpus order and train them concurrently, racing on the tables with
+ * red.global.add (Hogwild).  lanes = 1 is the sequential statement of the algorithm (bit-exact
+ * against the oracle); lanes = 0 / chunk_walks = 0 pick gw_sgns_auto_shape().
+ * Pair q = 2i + (j>i) of walk w draws its K negatives from Philox4x32-10(ctr {lo32(w), hi32(w),
+ * (q<<4)|c, (ep<<8)|0x53}, key = seed): negative t uses words 2(t-1), 2(t-1)+1:
  * slot = mulhi32(x0, n), u = (x1>>8)*2^-24, target = u < prob[slot] ? slot : alias[slot];
- * a draw equal to the centre is skipped.  Update rule = gensim w2v_fast_sentence_sg_neg.
- * Hogwild: one thread per walk, updates by red.global.add.v4.f32.  max_threads = 0 picks the
- * occupancy-derived grid; max_threads = 1 is the deterministic sequential mode used by the parity
- * tests (bit-exact against the oracle).  d in {8,16,32}; K <= 32; L <= 4096.
+ * a draw equal to the centre is skipped.  Update rule = gensim w2v_fast_sentence_sg_neg, all
+ * arithmetic unfused fp32; the dot product sums d/2 (<= 32) chunks left to right and combines the
+ * chunk sums by a pairwise tree.  d in {8,16,32,64,128}; K <= 32; L <= 4096.
  * A negative token ends its walk early (ragged corpora are padded with -1). */
 int gw_sgns_train(int32_t n, int32_t d, const int32_t *tokens, int64_t W, int32_t L,
                   int32_t window, int32_t K, int32_t epochs, int32_t epoch_begin,
                   int32_t epoch_end, double alpha0, double alpha_min, int64_t job_walks,
-                  const gw_alias_entry *alias_table, float *syn0, float *syn1neg, uint64_t seed,
-                  int64_t max_threads, gw_stream_t stream);
+                  int64_t chunk_walks, const gw_alias_entry *alias_table, float *syn0,
+                  float *syn1neg, uint64_t seed, int64_t lanes, gw_stream_t stream);
+
+/* the (lanes, chunk_walks) gw_sgns_train uses when they are passed as 0 (host pointers) */
+int gw_sgns_auto_shape(int32_t n, int64_t W, int64_t job_walks, int64_t *lanes_out,
+                       int64_t *chunk_out);
 
 /* ---- (4) similarity statistics ------------------------------------------------------------ */
 

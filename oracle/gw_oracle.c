@@ -171,6 +171,25 @@ static inline int32_t bisect_left_u32(const uint32_t *a, int32_t lo, int32_t hi,
     return lo;
 }
 
+/* Dot product in the summation order of the CUDA kernel (gensim calls BLAS sdot, whose order is
+ * implementation-defined): the row is split into G = min(32, d/2) chunks (d a power of two >= 4;
+ * otherwise one chunk), each chunk summed left to right, chunk sums combined by a pairwise tree. */
+static float dot_rows(const float *a, const float *b, int d)
+{
+    int G = 1;
+    if (d >= 4 && (d & (d - 1)) == 0) G = d / 2 > 32 ? 32 : d / 2;
+    const int E = d / G;
+    float c[32];
+    for (int g = 0; g < G; ++g) {
+        float s = a[g * E] * b[g * E];
+        for (int k = 1; k < E; ++k) s = s + a[g * E + k] * b[g * E + k];
+        c[g] = s;
+    }
+    for (int m = 1; m < G; m <<= 1)
+        for (int g = 0; g < G; g += 2 * m) c[g] = c[g] + c[g + m];
+    return c[0];
+}
+
 /* one (centre, context) pair: gensim w2v_fast_sentence_sg_neg (word2vec_inner.pyx) */
 static void pair_update(int sampler, draw_state *ds, int32_t V, int32_t d, int32_t K,
                         int32_t centre, int32_t context, float alpha, const float *exp_table,
@@ -206,8 +225,7 @@ static void pair_update(int sampler, draw_state *ds, int32_t V, int32_t d, int32
             label = 0.0f;
         }
         float *row2 = syn1neg + (int64_t)target * d;
-        float f = 0.0f;
-        for (int k = 0; k < d; ++k) f = f + row1[k] * row2[k];
+        const float f = dot_rows(row1, row2, d);
         if (f <= -(float)GWO_MAX_EXP || f >= (float)GWO_MAX_EXP) continue;
         const float sig =
             exp_table[(int)((double)(f + (float)GWO_MAX_EXP) *

@@ -159,7 +159,7 @@ def test_word2vec_on_plain_list_corpus_ragged():
     walks = [['a', 'b', 'c'], ['b', 'a'], ['c', 'b', 'a', 'b'], ['d']] * 50
     dw = DeepWalk(nx.MultiGraph())
     dw.walks = walks
-    dw.word2vec(max_threads=1, sgns_seed=3)
+    dw.word2vec(lanes=1, sgns_seed=3)
     wv = dw.model.wv
     assert wv.index_to_key[0] == 'b' and sorted(wv.index_to_key) == ['a', 'b', 'c', 'd']
     assert [wv.get_vecattr(k, 'count') for k in ('a', 'b', 'c', 'd')] == [150, 200, 100, 50]

@@ -246,16 +246,16 @@ def sgns_case(n, m, niter, L, d, K, epochs, seed):
     return tok, prob, alias, syn0, syn1
 
 
-def gpu_sgns(tok, n, d, K, epochs, prob, alias, syn0, syn1, seed, max_threads, job_walks=1000,
-             alpha0=0.025, alpha_min=0.0001):
+def gpu_sgns(tok, n, d, K, epochs, prob, alias, syn0, syn1, seed, lanes, job_walks=1000,
+             alpha0=0.025, alpha_min=0.0001, chunk_walks=0):
     L, W = tok.shape
     table = np.empty((n, 2), dtype=np.int32)
     table[:, 0] = prob.view(np.int32)
     table[:, 1] = alias
     d0, d1 = dev(syn0), dev(syn1)
     _lib.call('gw_sgns_train', n, d, _lib.ptr(dev(tok, np.int32)), W, L, 1, K, epochs, 0, epochs,
-              alpha0, alpha_min, job_walks, _lib.ptr(dev(table)), _lib.ptr(d0), _lib.ptr(d1), seed,
-              max_threads, st())
+              alpha0, alpha_min, job_walks, chunk_walks, _lib.ptr(dev(table)), _lib.ptr(d0), _lib.ptr(d1),
+              seed, lanes, st())
     torch.cuda.synchronize()
     return d0.cpu().numpy(), d1.cpu().numpy()
 
@@ -271,7 +271,7 @@ def test_sgns_sequential_bit_exact(n, m, niter, L, d, K, epochs):
     want0, want1 = syn0.copy(), syn1.copy()
     olib.sgns_train(tok, n, d, want0, want1, sampler=1, K=K, epochs=epochs, job_walks=100,
                     alias_prob=prob, alias_idx=alias, seed=seed)
-    got0, got1 = gpu_sgns(tok, n, d, K, epochs, prob, alias, syn0, syn1, seed, max_threads=1,
+    got0, got1 = gpu_sgns(tok, n, d, K, epochs, prob, alias, syn0, syn1, seed, lanes=1,
                           job_walks=100)
     assert np.array_equal(got0.view(np.uint32), want0.view(np.uint32))
     assert np.array_equal(got1.view(np.uint32), want1.view(np.uint32))
@@ -288,7 +288,7 @@ def test_sgns_ragged_walks_bit_exact():
     want0, want1 = syn0.copy(), syn1.copy()
     olib.sgns_train(tok, n, d, want0, want1, sampler=1, K=K, epochs=1, alias_prob=prob,
                     alias_idx=alias, seed=5)
-    got0, got1 = gpu_sgns(tok, n, d, K, 1, prob, alias, syn0, syn1, 5, max_threads=1)
+    got0, got1 = gpu_sgns(tok, n, d, K, 1, prob, alias, syn0, syn1, 5, lanes=1)
     assert np.array_equal(got0, want0) and np.array_equal(got1, want1)
 
 
@@ -300,22 +300,36 @@ def test_sgns_unsupported_raises():
 
 
 def test_sgns_hogwild_close_to_sequential():
-    """Hogwild run (64 walks in flight on a 200-node graph) vs the sequential oracle on the same
-    corpus/negatives: rows differ by reordering of float adds and stale reads only; the similarity
-    structure of the two solutions agrees."""
+    """Concurrent workers (16 workers, 25-walk chunks on a 200-node graph) vs the sequential oracle on
+    the same corpus and negatives: the runs differ only by stale reads and the order of float adds;
+    the neighbour-similarity distributions agree."""
+    from scipy.stats import ks_2samp
     n, d, K, epochs = 200, 8, 5, 5
     tok, prob, alias, syn0, syn1 = sgns_case(n, 1500, 20, 10, d, K, epochs, seed=21)
     want0, want1 = syn0.copy(), syn1.copy()
     olib.sgns_train(tok, n, d, want0, want1, sampler=1, K=K, epochs=epochs, alias_prob=prob,
                     alias_idx=alias, seed=77)
-    got0, _ = gpu_sgns(tok, n, d, K, epochs, prob, alias, syn0, syn1, 77, max_threads=64)
+    got0, _ = gpu_sgns(tok, n, d, K, epochs, prob, alias, syn0, syn1, 77, lanes=16, chunk_walks=25)
     assert np.isfinite(got0).all()
-    # pairwise cosine structure agrees: compare similarity of neighbours
     row_ptr, col_idx = graphs.csr_arrays(n, 1500, seed=21, self_loops=2)
     s_want = stats_ref.null_similarities(row_ptr, col_idx, want0)
     s_got = stats_ref.null_similarities(row_ptr, col_idx, got0)
-    assert np.corrcoef(s_want, s_got)[0, 1] > 0.9
-    assert abs(s_want.mean() - s_got.mean()) < 0.05
+    assert ks_2samp(s_want, s_got).statistic < 0.08
+    assert abs(s_want.mean() - s_got.mean()) < 0.03
+
+
+def test_sgns_chunk_must_divide_job():
+    tok, prob, alias, syn0, syn1 = sgns_case(20, 50, 1, 5, 8, 5, 1, seed=1)
+    with pytest.raises(ValueError):
+        gpu_sgns(tok, 20, 8, 5, 1, prob, alias, syn0, syn1, 1, lanes=4, chunk_walks=300)
+
+
+def test_sgns_auto_shape():
+    lanes, chunk = ctypes.c_int64(0), ctypes.c_int64(0)
+    for n, W in ((2300, 3465000), (38000, 152681600), (1000000, 1000000000), (3, 400)):
+        _lib.call('gw_sgns_auto_shape', n, W, 1000, ctypes.byref(lanes), ctypes.byref(chunk))
+        assert 1 <= lanes.value <= max(1, n // 2) and 1000 % chunk.value == 0
+        assert lanes.value * chunk.value <= max(W // 50, chunk.value)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -77,8 +77,7 @@ def oracle_vectors(row_ptr, col_idx, walk_seed, sgns_seed, mode, nthreads=1):
         vec = np.zeros((n, D), dtype=np.float32)
         vec[itn] = syn0
         return vec
-    stride = coprime_stride(int(row_ptr[-1]))
-    tok = olib.walk_uniform(row_ptr, col_idx, NITER, WL, walk_seed, stride)
+    tok = olib.walk_uniform(row_ptr, col_idx, NITER, WL, walk_seed, 0)   # corpus order
     counts = np.bincount(tok.ravel(), minlength=n)
     prob, alias = olib.alias_table(counts)
     order = np.argsort(-counts, kind='stable')
@@ -143,20 +142,20 @@ def run_gpu(a):
                 dw = DeepWalk(csr, WL, NITER, seed=mix(seed, 0, rep))
                 dw.get_walks()
                 dw.word2vec(vector_size=D, negative=K, epochs=EPOCHS, sgns_seed=mix(seed, 1, rep),
-                            max_threads=conc)
+                            lanes=conc, chunk_walks=a.chunk)
                 sims = gw.pair_similarities(dw.model.wv, pairs).cpu().numpy()
                 torch.cuda.synchronize(); dt = time.time() - t0
-                np.save(os.path.join(a.out, '%s_gpu-%d_s%d_real%d.npy' % (a.case, conc, seed, rep)), sims)
+                np.save(os.path.join(a.out, '%s_gpu-%s%d_s%d_real%d.npy' % (a.case, a.tag, conc, seed, rep)), sims)
                 del dw
                 t1 = time.time()
                 rg = get_rand_graph(mg, seed=mix(seed, 2, rep), materialize=False)
                 dw = DeepWalk(rg, WL, NITER, seed=mix(seed, 3, rep))
                 dw.get_walks()
                 dw.word2vec(vector_size=D, negative=K, epochs=EPOCHS, sgns_seed=mix(seed, 4, rep),
-                            max_threads=conc)
+                            lanes=conc, chunk_walks=a.chunk)
                 null = np.asarray(get_null_distributions(rg, dw.model.wv), dtype=np.float32)
                 torch.cuda.synchronize(); dt2 = time.time() - t1
-                np.save(os.path.join(a.out, '%s_gpu-%d_s%d_null%d.npy' % (a.case, conc, seed, rep)), null)
+                np.save(os.path.join(a.out, '%s_gpu-%s%d_s%d_null%d.npy' % (a.case, a.tag, conc, seed, rep)), null)
                 del dw, rg
                 timings['%d/%d/%d' % (conc, seed, rep)] = [dt, dt2]
                 print('gpu conc=%d seed %d rep %d: real %.2fs null %.2fs' % (conc, seed, rep, dt, dt2),
@@ -217,6 +216,8 @@ def main():
     ap.add_argument('--seeds', default='0,1,2')
     ap.add_argument('--nreps', type=int, default=2)
     ap.add_argument('--conc', default='0')
+    ap.add_argument('--chunk', type=int, default=0)
+    ap.add_argument('--tag', default='')
     ap.add_argument('--procs', type=int, default=os.cpu_count())
     ap.add_argument('--out', default='gpurun_out/study')
     ap.add_argument('--ref', default='oracle-gensim')
