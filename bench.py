@@ -116,7 +116,7 @@ def run_reference(args):
     graphs, n, u, v, is_go, ng = build_inputs(args.scale)
     row_ptr, col_idx = graphs.csr_from_edges_numpy(n, u, v)
     from oracle import lib as olib
-    threads = olib.lib().gwo_lanes()
+    threads = olib.lib().gwo_max_threads()
     vals, sample = [], ''
     t_all = time.perf_counter()
     for i in range(args.warmup + args.steps):
@@ -288,7 +288,7 @@ def run_ours(args):
                 'e2e': {'value': e2e_value, 'unit': 'pairs/s', 'h2d_bytes_per_step': int(h2d),
                         'd2h_bytes_per_step': int(d2h), 'ms_per_step': 1e3 * float(t_e.item()) / args.steps},
                 'gpu_launches': int(launches),
-                'roofline': {'kernel': 'sgns_train_kernel<8,5> (one epoch per launch)',
+                'roofline': {'kernel': 'sgns_train_kernel<8,4,5> (one epoch per launch)',
                              'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                              'frac': achieved / peak, 'traffic': traffic,
                              'peak_source': 'measured (MEASURED_PEAKS.json hbm_gbs)' if peaks else 'fallback',
@@ -299,11 +299,12 @@ def run_ours(args):
                 'walk': {'steps_per_s': W * (WL - 1) / (walk_ms / 1e3), 'ms': walk_ms,
                          'achieved_gbs': BYTES_PER_STEP * W * (WL - 1) / (walk_ms / 1e3) / 1e9},
                 'sgns_kernel_pairs_per_s': pairs_launch / (k_avg / 1e3),
-                'lanes': args.lanes}
+                'sgns_shape': {'lanes': dv['lanes'], 'chunk_walks': dv['chunk_walks'],
+                               'job_walks': dv['job_walks']}}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import lib as olib
         csr.to_host()
-        threads = olib.lib().gwo_lanes()
+        threads = olib.lib().gwo_max_threads()
         rate, sample = cpu_sample_rate(csr.row_ptr, csr.col_idx, threads)
         line['cpu_baseline'] = {'value': rate, 'unit': 'pairs/s', 'cores': threads, 'kind': 'port',
                                 'sample': sample}

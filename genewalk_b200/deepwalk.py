@@ -313,6 +313,14 @@ class DeepWalk(object):
         _lib.call('gw_sgns_init', n, d, _lib.ptr(rank_of_node), _lib.ptr(rng_rows), _lib.ptr(syn0),
                   _lib.ptr(syn1neg), st)
         job_walks = max(1, int(batch_words) // max(L, 1))
+        if int(lanes) == 0 or int(chunk_walks) == 0:
+            import ctypes
+            a_l, a_c = ctypes.c_int64(0), ctypes.c_int64(0)
+            _lib.call('gw_sgns_auto_shape', n, W, job_walks, ctypes.byref(a_l), ctypes.byref(a_c))
+            if int(lanes) == 0:
+                lanes = a_l.value
+            if int(chunk_walks) == 0:
+                chunk_walks = job_walks if int(lanes) == 1 else a_c.value
         for ep in range(int(epochs)):
             if epoch_hook is not None:
                 epoch_hook(ep, 'before')
@@ -325,6 +333,7 @@ class DeepWalk(object):
         return {'nodes': nodes, 'n': n, 'W': W, 'L': L, 'syn0': syn0, 'syn1neg': syn1neg,
                 'counts': counts, 'rank_of_node': rank_of_node, 'node_of_rank': node_of_rank,
                 'n_vocab': n_vocab, 'alias': alias, 'rng_rows': rng_rows,
+                'lanes': int(lanes), 'chunk_walks': int(chunk_walks), 'job_walks': job_walks,
                 'h2d_bytes': rows.nbytes}
 
 

@@ -18,13 +18,15 @@ scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
 lanes_list = [int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else \
     [2048, 4096, 9472, 18944]
 chunk = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+stride = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 n, u, v, is_go = graphs.human_scale_edges(seed=2, n_genes=int(20000 * scale), n_go=int(18000 * scale),
                                           n_gene_edges=int(700000 * scale), n_annot=int(250000 * scale),
                                           n_isa=int(50000 * scale), n_modules=max(4, int(500 * scale)))
 rp, ci = graphs.csr_from_edges_numpy(n, u, v)
 csr = GraphCSR(['v%d' % i for i in range(n)], rp, ci).to_device()
 dw = DeepWalk(csr, 10, 100, seed=1)
-dw.get_walks()
+from genewalk_b200.csr import coprime_stride
+dw.get_walks(stride=coprime_stride(csr.nnz) if stride < 0 else stride)
 W = len(dw.walks)
 pairs = W * 18
 out = {'n': n, 'A': csr.nnz, 'W': W, 'pairs_per_epoch': pairs, 'lanes': {}}
