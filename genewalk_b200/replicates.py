@@ -1,0 +1,201 @@
+"""Replicate driver: the loops of /root/reference/genewalk/cli.py:200-214 (nreps_graph real-network
+replicates) and :219-238 (nreps_null randomized-network replicates, pooled and sorted null
+similarities), sharded one replicate per GPU.
+
+Replicates are independent units: unit u runs on rank u % world_size with no
+data-path collective; the only exchange is one all-gather of (a) the fixed-length gene-GO similarity
+vector of every real replicate and (b) the variable-length null-similarity array of every null
+replicate, after which every rank holds everything the statistics step needs.  With
+``torch.distributed`` initialised on NCCL the gathers run over NVLink; the host logic is backend-
+agnostic (the CPU tests drive it over gloo).
+"""
+import logging
+import random
+
+import numpy as np
+
+from . import _lib
+from .csr import GraphCSR
+from .deepwalk import DeepWalk
+from .null_distributions import get_rand_graph
+from .perform_statistics import GeneWalk
+
+logger = logging.getLogger('genewalk.replicates')
+
+KIND_REAL, KIND_NULL = 0, 1
+
+
+def mix_seed(base_seed, stream, rep):
+    """splitmix64 finaliser over (base_seed, stream, rep) -> independent 64-bit seeds."""
+    m = 2 ** 64
+    x = (base_seed * 0x9E3779B97F4A7C15 + stream * 0xBF58476D1CE4E5B9 +
+         rep * 0x94D049BB133111EB + 1) % m
+    x ^= x >> 30
+    x = (x * 0xBF58476D1CE4E5B9) % m
+    x ^= x >> 27
+    x = (x * 0x94D049BB133111EB) % m
+    x ^= x >> 31
+    return x
+
+
+def plan_units(nreps_graph, nreps_null, world_size=1, rank=0):
+    """Units of this rank: [(kind, rep)], round-robin over real replicates then null replicates."""
+    units = [(KIND_REAL, r) for r in range(nreps_graph)] + [(KIND_NULL, r) for r in range(nreps_null)]
+    return [u for i, u in enumerate(units) if i % world_size == rank]
+
+
+def owner_of(kind, rep, nreps_graph, world_size):
+    idx = rep if kind == KIND_REAL else nreps_graph + rep
+    return idx % world_size
+
+
+# ---------------------------------------------------------------------------------------------
+# collectives (work on CPU tensors over gloo and CUDA tensors over NCCL)
+# ---------------------------------------------------------------------------------------------
+def _dist():
+    import torch.distributed as dist
+    return dist if dist.is_available() and dist.is_initialized() else None
+
+
+def world():
+    d = _dist()
+    return (d.get_world_size(), d.get_rank()) if d is not None else (1, 0)
+
+
+def gather_varlen(t, group=None):
+    """All ranks get the list [t_rank0, t_rank1, ...] of 1-D tensors of different lengths."""
+    import torch
+    d = _dist()
+    if d is None:
+        return [t]
+    ws = d.get_world_size(group)
+    n = torch.tensor([t.numel()], dtype=torch.int64, device=t.device)
+    sizes = [torch.zeros_like(n) for _ in range(ws)]
+    d.all_gather(sizes, n, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    cap = max(max(sizes), 1)
+    pad = torch.zeros(cap, dtype=t.dtype, device=t.device)
+    pad[:t.numel()] = t
+    out = [torch.empty_like(pad) for _ in range(ws)]
+    d.all_gather(out, pad, group=group)
+    return [o[:s] for o, s in zip(out, sizes)]
+
+
+def gather_fixed(t, group=None):
+    """All ranks get the list of same-shaped tensors [t_rank0, ...]."""
+    import torch
+    d = _dist()
+    if d is None:
+        return [t]
+    out = [torch.empty_like(t) for _ in range(d.get_world_size(group))]
+    d.all_gather(out, t.contiguous(), group=group)
+    return out
+
+
+def exchange_results(local_sims, local_null, nreps_graph, nreps_null, m, device, group=None):
+    """local_sims: {rep: tensor[m]}, local_null: {rep: tensor[len]} of this rank's units ->
+    (sims [nreps_graph, m], [null_rep0, null_rep1, ...]) on every rank."""
+    import torch
+    ws, rank = world()
+    per_rank_real = (nreps_graph + ws - 1) // ws
+    # fixed-length: slot k of a rank holds its k-th real replicate (zeros when it has none)
+    mine = torch.zeros((max(per_rank_real, 1), m), dtype=torch.float32, device=device)
+    my_real = sorted(local_sims)
+    for k, rep in enumerate(my_real):
+        mine[k] = local_sims[rep]
+    gathered = gather_fixed(mine, group)
+    sims = torch.zeros((nreps_graph, m), dtype=torch.float32, device=device)
+    for rep in range(nreps_graph):
+        own = owner_of(KIND_REAL, rep, nreps_graph, ws)
+        k = [r for r in range(nreps_graph) if owner_of(KIND_REAL, r, nreps_graph, ws) == own].index(rep)
+        sims[rep] = gathered[own][k]
+    # variable-length: every rank concatenates its null arrays, lengths travel alongside
+    my_null = sorted(local_null)
+    lens = torch.tensor([local_null[r].numel() for r in my_null] or [0], dtype=torch.int64,
+                        device=device)
+    flat = torch.cat([local_null[r].reshape(-1) for r in my_null]) if my_null else \
+        torch.zeros(0, dtype=torch.float32, device=device)
+    all_flat = gather_varlen(flat, group)
+    all_lens = gather_varlen(lens, group)
+    nulls = [None] * nreps_null
+    for rk in range(ws):
+        reps = [r for r in range(nreps_null) if owner_of(KIND_NULL, r, nreps_graph, ws) == rk]
+        off = 0
+        for k, rep in enumerate(reps):
+            ln = int(all_lens[rk][k].item())
+            nulls[rep] = all_flat[rk][off:off + ln]
+            off += ln
+    return sims, nulls
+
+
+# ---------------------------------------------------------------------------------------------
+# the replicate bodies
+# ---------------------------------------------------------------------------------------------
+def real_replicate(csr, base_seed, rep, dim_rep=8, walk_length=10, niter=100, **w2v):
+    """cli.py:202-203: run_walks(MG.graph, workers, vector_size) -> DeepWalk (model.wv on host)."""
+    dw = DeepWalk(csr, walk_length, niter, seed=mix_seed(base_seed, 0, rep))
+    dw.get_walks()
+    dw.word2vec(vector_size=dim_rep, sgns_seed=mix_seed(base_seed, 1, rep), **w2v)
+    return dw
+
+
+def null_replicate(mg_or_degrees, base_seed, rep, dim_rep=8, walk_length=10, niter=100, **w2v):
+    """cli.py:221-235: get_rand_graph -> run_walks -> get_null_distributions, all on the device.
+    Returns (device float32 tensor of null similarities, DeepWalk)."""
+    import ctypes
+    import torch
+    rg = get_rand_graph(mg_or_degrees, seed=mix_seed(base_seed, 2, rep), materialize=False)
+    dw = DeepWalk(rg, walk_length, niter, seed=mix_seed(base_seed, 3, rep))
+    dw.get_walks()
+    if len(dw.walks) == 0:
+        return torch.zeros(0, dtype=torch.float32, device='cuda'), dw
+    dv = dw.train_device(vector_size=dim_rep, sgns_seed=mix_seed(base_seed, 4, rep), **w2v)
+    csr = rg.csr
+    sims = torch.empty(csr.nnz, dtype=torch.float32, device=dv['syn0'].device)
+    cnt = ctypes.c_int64(0)
+    _lib.call('gw_null_similarities', csr.n, _lib.ptr(csr.d_row_ptr), _lib.ptr(csr.d_col_idx),
+              int(dim_rep), _lib.ptr(dv['syn0']), _lib.ptr(sims), ctypes.byref(cnt), _lib.stream_ptr())
+    return sims[:cnt.value], dw
+
+
+def run_genewalk(mg, genes, nreps_graph=3, nreps_null=3, alpha_fdr=1, gene_id_type='hgnc_symbol',
+                 dim_rep=8, base_seed=None, group=None, return_parts=False, **w2v):
+    """node_vectors + null_distribution + statistics stages of cli.run_main (cli.py:194-252) for an
+    assembled ``nx.MultiGraph``; replicates are sharded over the ranks of the initialised process
+    group (one process per GPU).  Returns the results DataFrame (identical on every rank)."""
+    import torch
+    _lib.require_cuda()
+    ws, rank = world()
+    if base_seed is None:
+        base_seed = random.getrandbits(64)
+        if ws > 1:   # all ranks must agree on the seed: rank 0's draw wins
+            t = torch.tensor([base_seed & (2 ** 63 - 1)], dtype=torch.int64, device='cuda')
+            _dist().broadcast(t, 0, group=group)
+            base_seed = int(t.item())
+    csr = GraphCSR.from_networkx(mg).to_device()
+    gw = GeneWalk(mg, genes, [], np.zeros(1, np.float32), gene_id_type=gene_id_type)
+    pairs = gw.collect_pairs()
+    m = len(pairs['pair_go'])
+    local_sims, local_null, nvs = {}, {}, {}
+    for kind, rep in plan_units(nreps_graph, nreps_null, ws, rank):
+        if kind == KIND_REAL:
+            logger.info('real replicate %d/%d on rank %d' % (rep + 1, nreps_graph, rank))
+            dw = real_replicate(csr, base_seed, rep, dim_rep, **w2v)
+            nvs[rep] = dw.model.wv
+            local_sims[rep] = gw.pair_similarities(dw.model.wv, pairs)
+        else:
+            logger.info('null replicate %d/%d on rank %d' % (rep + 1, nreps_null, rank))
+            local_null[rep], _ = null_replicate(mg, base_seed, rep, dim_rep, **w2v)
+    dev = torch.device('cuda')
+    sims, nulls = exchange_results(local_sims, local_null, nreps_graph, nreps_null, m, dev, group)
+    pooled = torch.cat(nulls) if nulls else torch.zeros(0, dtype=torch.float32, device=dev)
+    if pooled.numel() > 0:   # cli.py:238: srd = np.asarray(sorted(srd))
+        pooled = pooled.contiguous()
+        _lib.call('gw_sort_f32', _lib.ptr(pooled), pooled.numel(), _lib.stream_ptr())
+    gw.srd = pooled.cpu().numpy()
+    gw._d_srd = pooled
+    gw.nvs = [nvs.get(r) for r in range(nreps_graph)]
+    df = gw.generate_output(alpha_fdr=alpha_fdr, sims=sims, pairs=pairs)
+    if return_parts:
+        return df, {'sims': sims, 'null': gw.srd, 'nvs': nvs, 'base_seed': base_seed}
+    return df

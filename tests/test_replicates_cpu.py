@@ -1,0 +1,88 @@
+"""CPU tests of the multi-GPU host logic: replicate sharding plan and the all-gather exchange of
+similarity arrays, run over gloo with world_size 2 (the GPU path uses the same code over NCCL)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from genewalk_b200 import replicates as R
+
+
+def test_plan_units_covers_everything_once():
+    for ng, nn in ((3, 3), (10, 10), (1, 0), (0, 2), (5, 2)):
+        for ws in (1, 2, 4, 8):
+            seen = []
+            for rank in range(ws):
+                units = R.plan_units(ng, nn, ws, rank)
+                assert all(R.owner_of(k, r, ng, ws) == rank for k, r in units)
+                seen += units
+            assert sorted(seen) == sorted([(R.KIND_REAL, r) for r in range(ng)] +
+                                          [(R.KIND_NULL, r) for r in range(nn)])
+            # balanced: 20 units on 8 GPUs -> 3 waves
+            sizes = [len(R.plan_units(ng, nn, ws, rank)) for rank in range(ws)]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_mix_seed_streams_are_distinct():
+    seeds = {R.mix_seed(b, s, r) for b in (0, 1, 2) for s in range(5) for r in range(10)}
+    assert len(seeds) == 150 and all(0 <= x < 2 ** 64 for x in seeds)
+
+
+def test_exchange_single_process_is_identity():
+    sims = {0: torch.arange(5, dtype=torch.float32), 1: torch.ones(5)}
+    null = {0: torch.tensor([0.5, 0.25]), 1: torch.zeros(0), 2: torch.tensor([1.0])}
+    s, n = R.exchange_results(sims, null, 2, 3, 5, torch.device('cpu'))
+    assert torch.equal(s[0], sims[0]) and torch.equal(s[1], sims[1])
+    assert [x.tolist() for x in n] == [[0.5, 0.25], [], [1.0]]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, ws, port, ng, nn, m, out):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=ws)
+    try:
+        # each rank fabricates the results of its own units: values encode (kind, rep)
+        local_sims, local_null = {}, {}
+        for kind, rep in R.plan_units(ng, nn, ws, rank):
+            if kind == R.KIND_REAL:
+                local_sims[rep] = torch.full((m,), float(rep)) + torch.arange(m) * 1e-3
+            else:
+                local_null[rep] = torch.full((10 + 3 * rep,), 100.0 + rep)
+        sims, nulls = R.exchange_results(local_sims, local_null, ng, nn, m, torch.device('cpu'))
+        ok = sims.shape == (ng, m)
+        for rep in range(ng):
+            ok &= bool(torch.allclose(sims[rep], torch.full((m,), float(rep)) + torch.arange(m) * 1e-3))
+        for rep in range(nn):
+            ok &= nulls[rep].numel() == 10 + 3 * rep and bool((nulls[rep] == 100.0 + rep).all())
+        parts = R.gather_varlen(torch.arange(rank + 1, dtype=torch.float32))
+        ok &= [p.numel() for p in parts] == list(range(1, ws + 1))
+        out[rank] = int(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('ng,nn', [(3, 3), (1, 4), (5, 0)])
+def test_exchange_over_gloo_world_size_2(ng, nn):
+    ws = 2
+    ctx = mp.get_context('spawn')
+    out = ctx.Array('i', [0] * ws)
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, ws, port, ng, nn, 7, out)) for r in range(ws)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert list(out) == [1] * ws
