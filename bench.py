@@ -299,7 +299,7 @@ def run_ours(args):
                 'walk': {'steps_per_s': W * (WL - 1) / (walk_ms / 1e3), 'ms': walk_ms,
                          'achieved_gbs': BYTES_PER_STEP * W * (WL - 1) / (walk_ms / 1e3) / 1e9},
                 'sgns_kernel_pairs_per_s': pairs_launch / (k_avg / 1e3),
-                'sgns_shape': {'lanes': dv['lanes'], 'chunk_walks': dv['chunk_walks'],
+                'sgns_shape': {'lanes': dv['lanes'], 'chunk_walks': dv['chunk_walks'], 'streams': dv['streams'],
                                'job_walks': dv['job_walks']}}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import lib as olib

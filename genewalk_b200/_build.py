@@ -4,7 +4,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-SO_PATH = os.path.join(HERE, 'libgenewalk_b200.so')
+SO_PATH = os.path.join(HERE, os.environ.get('GW_SO_NAME', 'libgenewalk_b200.so'))
 SOURCES = ['gw_scan_sort.cu', 'gw_walk.cu', 'gw_sgns.cu', 'gw_sgns_train.cu', 'gw_graph.cu', 'gw_stats.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-fmad=false',  # every fp op rounds on its own: bit-exact against the oracle
@@ -31,7 +31,8 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return SO_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + \
+    cmd = [_nvcc()] + NVCC_FLAGS + os.environ.get('GW_EXTRA_NVCC_FLAGS', '').split() + \
+          (['-Xptxas', '-v'] if verbose else []) + \
           [os.path.join(CSRC, f) for f in SOURCES] + ['-o', SO_PATH]
     env = dict(os.environ)
     env.setdefault('NVCC_CCBIN', '/usr/bin/g++')

@@ -29,7 +29,24 @@ namespace gw {
 
 constexpr int kExpTableSize = 1000;
 constexpr float kMaxExp = 6.0f;
-constexpr int kTrainThreads = 128;
+constexpr int kTrainThreads = 512;      // upper bound of the CTA size (launch bounds)
+constexpr int kSmemAliasMaxN = 56000;   // 4 B/entry packed alias table + EXP_TABLE fit 227 KB
+
+#ifdef GW_DEBUG_BLOWUP
+__device__ unsigned long long g_dbg[16];
+__device__ __forceinline__ void dbg_record(int site, int a, int b, float x, float y, float z)
+{
+    if (atomicCAS(&g_dbg[0], 0ULL, 1ULL) == 0ULL) {
+        g_dbg[1] = (unsigned long long)site; g_dbg[2] = (unsigned long long)(unsigned)a;
+        g_dbg[3] = (unsigned long long)(unsigned)b; g_dbg[4] = (unsigned long long)__float_as_uint(x);
+        g_dbg[5] = (unsigned long long)__float_as_uint(y); g_dbg[6] = (unsigned long long)__float_as_uint(z);
+        g_dbg[7] = (unsigned long long)(blockIdx.x * blockDim.x + threadIdx.x);
+    }
+}
+#define GW_DBG(site, a, b, x, y, z) do { if (!(fabsf(x) < 1e4f) || !(fabsf(y) < 1e4f) || !(fabsf(z) < 1e4f)) dbg_record(site, a, b, x, y, z); } while (0)
+#else
+#define GW_DBG(site, a, b, x, y, z) do { } while (0)
+#endif
 
 struct TrainParams {
     const int32_t *tokens;
@@ -44,6 +61,8 @@ struct TrainParams {
     double alpha_min;
     int64_t job_walks;    // walks per learning-rate job (gensim: 1000 walks of 10 words)
     int64_t chunk_walks;  // walks a worker takes from the queue at a time (divides job_walks)
+    int64_t streams;      // corpus slices the queue deals chunks from in turn (see gw_sgns_train)
+    int64_t stream_chunks;  // chunks per slice
     unsigned long long *job_queue;  // next job to hand out (device counter, zeroed per launch)
     const gw_alias_entry *alias;
     const float *exp_table;  // [1000] device copy of gensim's EXP_TABLE
@@ -95,13 +114,19 @@ __device__ __forceinline__ float group_dot(const float (&a)[E], const float (&b)
     return s;
 }
 
+// acceptance threshold of an alias slot for the 16-bit coin x1 >> 16
+__device__ __forceinline__ uint32_t coin_threshold(float prob)
+{
+    const uint32_t t = (uint32_t)floorf(__fmul_rn(prob, 65536.0f));
+    return t > 65535u ? 65535u : t;
+}
+
 __device__ __forceinline__ int32_t draw_negative(const TrainParams &P, uint32_t x0, uint32_t x1)
 {
     const int32_t slot = (int32_t)__umulhi(x0, (uint32_t)P.n);
-    const float u = (float)(x1 >> 8) * (1.0f / 16777216.0f);
     // the alias table is read-only for the whole kernel: non-coherent path, L1-cacheable
     const int2 e = __ldg(reinterpret_cast<const int2 *>(P.alias) + slot);
-    return u < __int_as_float(e.x) ? slot : e.y;
+    return (x1 >> 16) < coin_threshold(__int_as_float(e.x)) ? slot : e.y;
 }
 
 // the K negative targets of pair q of walk w in this epoch (every lane of the group computes them)
@@ -121,9 +146,13 @@ __device__ __forceinline__ void draw_targets(const TrainParams &P, int K, uint32
     }
 }
 
+// gensim: EXP_TABLE[(int)((f + MAX_EXP) * (EXP_TABLE_SIZE / MAX_EXP / 2))].  For the largest floats
+// below 6 the float sum f + 6 rounds up to 12 and the index becomes 1000, one past the table (gensim
+// then reads whatever follows EXP_TABLE in memory); the index is clamped to the last entry here.
 __device__ __forceinline__ int sigmoid_index(float f)
 {
-    return (int)((double)__fadd_rn(f, kMaxExp) * ((double)kExpTableSize / 6.0 / 2.0));
+    const int i = (int)((double)__fadd_rn(f, kMaxExp) * ((double)kExpTableSize / 6.0 / 2.0));
+    return i < kExpTableSize ? i : kExpTableSize - 1;
 }
 
 // ---- one (centre, context) pair, one target at a time (any K; also the hazard path) -------------
@@ -164,31 +193,41 @@ __device__ __forceinline__ void pair_sequential(const TrainParams &P, const floa
 // A step needs 2*KT negatives = 2*ceil(KT/2) Philox calls.  Call c (pair c / CP, call c % CP of
 // that pair, CP = ceil(KT/2)) is computed by lane c % G, which also resolves the call's (up to) two
 // negatives through the alias table; resolve() then hands every lane all 2*KT targets by shuffles.
-template <int G, int KT> struct StepDraw {
+template <int G, int KT, bool kSmemAlias> struct StepDraw {
     static constexpr int CP = (KT + 1) / 2;            // Philox calls per pair
     static constexpr int NC = 2 * CP;                  // calls per step
     static constexpr int R = (NC + G - 1) / G;         // calls per lane (rounds)
     int32_t slot[R][2];                                // this lane's draws: alias slot ...
-    float u[R][2];                                     // ... its coin ...
+    uint32_t coin[R][2];                               // ... its 16-bit coin ...
     int2 entry[R][2];                                  // ... and the alias entry (load in flight)
 
-    __device__ __forceinline__ void issue(const TrainParams &P, int sub, uint32_t w_lo, uint32_t w_hi,
-                                          uint32_t q_first)
+    // s_alias: packed (threshold << 16 | alias) copy of the table in shared memory, or unused
+    __device__ __forceinline__ void issue(const TrainParams &P, const uint32_t *s_alias, int sub,
+                                          uint32_t w_lo, uint32_t w_hi, uint32_t q_first)
     {
         const uint32_t ctr3 = ((uint32_t)P.epoch << 8) | kStreamSgns;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int c = sub + r * G;                 // call id of this lane in round r
             const int pair = c / CP, call = c - pair * CP;
-            const u32x4 x = philox4x32_10(w_lo, w_hi, ((q_first + (uint32_t)pair) << 4) | (uint32_t)call,
-                                          ctr3, P.key0, P.key1);
-            slot[r][0] = (int32_t)__umulhi(x.x, (uint32_t)P.n);
-            slot[r][1] = (int32_t)__umulhi(x.z, (uint32_t)P.n);
-            u[r][0] = (float)(x.y >> 8) * (1.0f / 16777216.0f);
-            u[r][1] = (float)(x.w >> 8) * (1.0f / 16777216.0f);
-            // the alias table is read-only for the whole kernel: non-coherent path, L1-cacheable
-            entry[r][0] = __ldg(reinterpret_cast<const int2 *>(P.alias) + slot[r][0]);
-            entry[r][1] = __ldg(reinterpret_cast<const int2 *>(P.alias) + slot[r][1]);
+            const bool used = c < NC;
+            const bool second = used && (2 * call + 1 < KT);   // the call's second negative exists
+            if (used) {
+                const u32x4 x = philox4x32_10(w_lo, w_hi, ((q_first + (uint32_t)pair) << 4) | (uint32_t)call,
+                                              ctr3, P.key0, P.key1);
+                slot[r][0] = (int32_t)__umulhi(x.x, (uint32_t)P.n);
+                slot[r][1] = (int32_t)__umulhi(x.z, (uint32_t)P.n);
+                coin[r][0] = x.y >> 16;
+                coin[r][1] = x.w >> 16;
+            }
+            if constexpr (kSmemAlias) {
+                if (used) entry[r][0].x = (int)s_alias[slot[r][0]];
+                if (second) entry[r][1].x = (int)s_alias[slot[r][1]];
+            } else {
+                // the alias table is read-only for the whole kernel: non-coherent path, L1-cacheable
+                if (used) entry[r][0] = __ldg(reinterpret_cast<const int2 *>(P.alias) + slot[r][0]);
+                if (second) entry[r][1] = __ldg(reinterpret_cast<const int2 *>(P.alias) + slot[r][1]);
+            }
         }
     }
 
@@ -198,8 +237,15 @@ template <int G, int KT> struct StepDraw {
 #pragma unroll
         for (int r = 0; r < R; ++r)
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
-                mine[r][j] = u[r][j] < __int_as_float(entry[r][j].x) ? slot[r][j] : entry[r][j].y;
+            for (int j = 0; j < 2; ++j) {
+                if constexpr (kSmemAlias) {
+                    const uint32_t e = (uint32_t)entry[r][j].x;
+                    mine[r][j] = coin[r][j] < (e >> 16) ? slot[r][j] : (int32_t)(e & 0xffffu);
+                } else {
+                    mine[r][j] = coin[r][j] < coin_threshold(__int_as_float(entry[r][j].x)) ? slot[r][j]
+                                                                                         : entry[r][j].y;
+                }
+            }
 #pragma unroll
         for (int x = 0; x < 2 * KT; ++x) {
             const int pair = x / KT, k = x - pair * KT;   // negative k of pair `pair`
@@ -272,6 +318,8 @@ __device__ __forceinline__ void step_update(const TrainParams &P, const float *s
             }
             if (ft <= -kMaxExp || ft >= kMaxExp) continue;
             const float g = __fmul_rn(__fsub_rn(t == 0 ? 1.0f : 0.0f, s_exp[sigmoid_index(ft)]), alpha);
+            GW_DBG(100 + t + (o ? 10 : 0), c, tg[x], ft, g, row[0]);
+            GW_DBG(200 + t + (o ? 10 : 0), c, tg[x], ctx[0], ctx[1], row[1]);
             float delta[E];
 #pragma unroll
             for (int k = 0; k < E; ++k) {
@@ -292,12 +340,21 @@ __device__ __forceinline__ void step_update(const TrainParams &P, const float *s
     }
 }
 
-template <int D, int G, int KT>
+template <int D, int G, int KT, bool kSmemAlias>
 __global__ void __launch_bounds__(kTrainThreads)
 sgns_train_kernel(const TrainParams P)
 {
-    __shared__ float s_exp[kExpTableSize];
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    float *s_exp = reinterpret_cast<float *>(s_raw);
+    uint32_t *s_alias = reinterpret_cast<uint32_t *>(s_raw + sizeof(float) * kExpTableSize);
     for (int i = threadIdx.x; i < kExpTableSize; i += blockDim.x) s_exp[i] = P.exp_table[i];
+    if constexpr (kSmemAlias) {
+        // packed copy of the noise table: (16-bit acceptance threshold << 16) | alias (n <= 56000)
+        for (int i = threadIdx.x; i < P.n; i += blockDim.x) {
+            const int2 e = __ldg(reinterpret_cast<const int2 *>(P.alias) + i);
+            s_alias[i] = (coin_threshold(__int_as_float(e.x)) << 16) | (uint32_t)e.y;
+        }
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int sub = lane & (G - 1);
@@ -309,8 +366,13 @@ sgns_train_kernel(const TrainParams P)
         unsigned long long chunk = 0;
         if (sub == 0) chunk = atomicAdd(P.job_queue, 1ULL);
         chunk = __shfl_sync(gmask, chunk, leader);
-        if (chunk >= (unsigned long long)nchunks) break;
-        const int64_t first = (int64_t)chunk * P.chunk_walks;
+        if (chunk >= (unsigned long long)(P.streams * P.stream_chunks)) break;
+        // the queue deals chunks from the `streams` corpus slices in turn, so the chunks in flight
+        // are consecutive inside each slice and at most lanes/streams workers share a start node
+        const int64_t slice = (int64_t)(chunk % (unsigned long long)P.streams);
+        const int64_t pos = slice * P.stream_chunks + (int64_t)(chunk / (unsigned long long)P.streams);
+        if (pos >= nchunks) continue;   // ragged last slice
+        const int64_t first = pos * P.chunk_walks;
         const int64_t last = first + P.chunk_walks < P.W ? first + P.chunk_walks : P.W;
         // gensim _get_next_alpha at pushed = job*job_walks examples (fp64, unfused, as the oracle);
         // chunk_walks divides job_walks, so a chunk lies inside one job
@@ -325,8 +387,8 @@ sgns_train_kernel(const TrainParams P)
             int32_t prev = -1, cur = __ldg(P.tokens + w);
             int32_t next = P.L > 1 ? __ldg(P.tokens + P.W + w) : -1;
             if constexpr (KT > 0) {
-                StepDraw<G, KT> draw;
-                draw.issue(P, sub, w_lo, w_hi, 0u);
+                StepDraw<G, KT, kSmemAlias> draw;
+                draw.issue(P, s_alias, sub, w_lo, w_hi, 0u);
                 for (int32_t i = 0; i < P.L && cur >= 0; ++i) {
                     // token two positions ahead (the next step's right context), loaded early
                     const int32_t next2 = (i + 2 < P.L && next >= 0) ? __ldg(P.tokens + (int64_t)(i + 2) * P.W + w) : -1;
@@ -343,7 +405,7 @@ sgns_train_kernel(const TrainParams P)
                     StepRows<D, G, KT> rows;
                     step_gather<D, G, KT>(P, sub, cur, prev, next, tg, rows);
                     // the next step's draws (Philox + alias loads) overlap this step's row gathers
-                    draw.issue(P, sub, w_lo, w_hi, 2u * (uint32_t)(i + 1));
+                    draw.issue(P, s_alias, sub, w_lo, w_hi, 2u * (uint32_t)(i + 1));
                     step_update<D, G, KT>(P, s_exp, sub, gmask, cur, prev, next, alpha, tg, rows);
                     prev = cur;
                     cur = next;
@@ -382,13 +444,33 @@ static void host_exp_table(float *t)
 template <int D, int G, int KT>
 static int launch_train(const TrainParams &P, int64_t lanes, cudaStream_t s)
 {
-    // `lanes` workers of G threads each, spread over all SMs in 128-thread CTAs
-    const int groups_per_block = kTrainThreads / G;
-    int64_t blocks = ceil_div<int64_t>(lanes, groups_per_block);
-    int block = kTrainThreads;
-    if (lanes < groups_per_block) block = (int)lanes * G;
+    // `lanes` workers of G threads each.  With the noise table in shared memory (n <= 56000) one
+    // CTA per SM holds lanes/num_sms workers (<= 512 threads); otherwise 128-thread CTAs.
+    const bool smem_alias = KT > 0 && P.n <= kSmemAliasMaxN;
+    const int sms = num_sms();
+    int block, blocks;
+    if (lanes * G <= 32) {
+        block = (int)lanes * G;
+        blocks = 1;
+    } else if (smem_alias) {
+        int64_t per_sm = ceil_div<int64_t>(lanes, sms) * G;
+        per_sm = ceil_div<int64_t>(per_sm, 32) * 32;
+        block = (int)(per_sm > kTrainThreads ? kTrainThreads : per_sm);
+        blocks = (int)ceil_div<int64_t>(lanes * G, block);
+        if (blocks > sms) blocks = sms;  // more would not be resident next to a 150+ KB table
+    } else {
+        block = 128;
+        blocks = (int)ceil_div<int64_t>(lanes * G, block);
+    }
+    size_t smem = sizeof(float) * kExpTableSize + (smem_alias ? sizeof(uint32_t) * (size_t)P.n : 0);
     GW_CUDA_OK(cudaMemsetAsync(P.job_queue, 0, sizeof(unsigned long long), s));
-    sgns_train_kernel<D, G, KT><<<(unsigned)blocks, block, 0, s>>>(P);
+    if (smem_alias) {
+        GW_CUDA_OK(cudaFuncSetAttribute(sgns_train_kernel<D, G, KT, true>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sgns_train_kernel<D, G, KT, true><<<blocks, block, smem, s>>>(P);
+    } else {
+        sgns_train_kernel<D, G, KT, false><<<blocks, block, smem, s>>>(P);
+    }
     GW_LAUNCH_OK();
     return GW_OK;
 }
@@ -405,32 +487,49 @@ static int64_t chunk_divisor(int64_t job_walks, int64_t want)
 
 }  // namespace gw
 
-// Default parallel shape.  Two fidelity constraints bound it: the walks in
-// flight (lanes*chunk) should span only ~2 % of the corpus, so that training still sweeps the corpus
-// in the reference's node-major order, and the number of workers should stay below ~n/2, so that
-// the Hogwild staleness per table row stays small; within them, as many workers as fill the GPU.
+// Default parallel shape.  Fidelity constraints (parity study, profiles/):
+// the Hogwild staleness per table row stays small when the workers stay below ~n/2 and at most
+// ~128 of them train walks that start at the same node; training keeps sweeping the corpus in the
+// reference's node-major order when few slices are active and the chunks in flight inside a slice
+// cover little more than one start node.  Within that: as many workers as fill the GPU.
+#ifdef GW_DEBUG_BLOWUP
+extern "C" int gw_debug_read(unsigned long long *out16)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, gw::g_dbg, sizeof(unsigned long long) * 16);
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(gw::g_dbg, z, sizeof z);
+    return 0;
+}
+#endif
+
 extern "C" int gw_sgns_auto_shape(int32_t n, int64_t W, int64_t job_walks, int64_t *lanes_out,
-                                  int64_t *chunk_out)
+                                  int64_t *chunk_out, int64_t *streams_out)
 {
     using namespace gw;
-    GW_REQUIRE(n > 0 && W > 0 && job_walks > 0 && lanes_out && chunk_out, "gw_sgns_auto_shape: bad arguments");
+    GW_REQUIRE(n > 0 && W > 0 && job_walks > 0 && lanes_out && chunk_out && streams_out,
+               "gw_sgns_auto_shape: bad arguments");
     int64_t lanes = (int64_t)num_sms() * 64;
     if (lanes > n / 2) lanes = n / 2;
-    const int64_t window = W / 50 > 0 ? W / 50 : 1;
-    const int64_t min_chunk = 8;
-    if (lanes * min_chunk > window) lanes = window / min_chunk;
     if (lanes < 1) lanes = 1;
-    int64_t chunk = chunk_divisor(job_walks, window / lanes);
+    const int64_t chunk = chunk_divisor(job_walks, 8);
+    const int64_t nchunks = ceil_div<int64_t>(W, chunk);
+    if (lanes > nchunks) lanes = nchunks;
+    int64_t streams = ceil_div<int64_t>(lanes, 128);
+    const int64_t max_streams = n / 50 > 0 ? n / 50 : 1;
+    if (streams > max_streams) streams = max_streams;
     *lanes_out = lanes;
     *chunk_out = chunk;
+    *streams_out = streams;
     return GW_OK;
 }
 
 extern "C" int gw_sgns_train(int32_t n, int32_t d, const int32_t *tokens, int64_t W, int32_t L,
                              int32_t window, int32_t K, int32_t epochs, int32_t epoch_begin,
                              int32_t epoch_end, double alpha0, double alpha_min, int64_t job_walks,
-                             int64_t chunk_walks, const gw_alias_entry *alias_table, float *syn0,
-                             float *syn1neg, uint64_t seed, int64_t lanes, gw_stream_t stream)
+                             int64_t chunk_walks, int64_t streams, const gw_alias_entry *alias_table,
+                             float *syn0, float *syn1neg, uint64_t seed, int64_t lanes,
+                             gw_stream_t stream)
 {
     using namespace gw;
     cudaStream_t s = (cudaStream_t)stream;
@@ -440,7 +539,8 @@ extern "C" int gw_sgns_train(int32_t n, int32_t d, const int32_t *tokens, int64_
     GW_REQUIRE(epochs >= 1 && epochs <= 65535 && epoch_begin >= 0 && epoch_begin <= epoch_end &&
                    epoch_end <= epochs,
                "gw_sgns_train: epochs=%d [%d,%d) invalid", epochs, epoch_begin, epoch_end);
-    GW_REQUIRE(job_walks >= 1 && lanes >= 0 && chunk_walks >= 0, "gw_sgns_train: job_walks/chunk_walks/lanes invalid");
+    GW_REQUIRE(job_walks >= 1 && lanes >= 0 && chunk_walks >= 0 && streams >= 0,
+               "gw_sgns_train: job_walks/chunk_walks/streams/lanes invalid");
     GW_REQUIRE(chunk_walks == 0 || (chunk_walks <= job_walks && job_walks % chunk_walks == 0),
                "gw_sgns_train: chunk_walks=%lld must divide job_walks=%lld", (long long)chunk_walks,
                (long long)job_walks);
@@ -454,12 +554,14 @@ extern "C" int gw_sgns_train(int32_t n, int32_t d, const int32_t *tokens, int64_
     }
     GW_REQUIRE((reinterpret_cast<uintptr_t>(syn0) & 15) == 0 && (reinterpret_cast<uintptr_t>(syn1neg) & 15) == 0,
                "gw_sgns_train: tables must be 16-byte aligned");
-    int64_t auto_lanes = 0, auto_chunk = 0;
-    GW_TRY(gw_sgns_auto_shape(n, W, job_walks, &auto_lanes, &auto_chunk));
+    int64_t auto_lanes = 0, auto_chunk = 0, auto_streams = 0;
+    GW_TRY(gw_sgns_auto_shape(n, W, job_walks, &auto_lanes, &auto_chunk, &auto_streams));
     if (lanes == 0) lanes = auto_lanes;
     if (chunk_walks == 0) chunk_walks = lanes == 1 ? job_walks : auto_chunk;
     const int64_t nchunks = ceil_div<int64_t>(W, chunk_walks);
     if (lanes > nchunks) lanes = nchunks;
+    if (streams == 0) streams = lanes == 1 ? 1 : (auto_streams < lanes ? auto_streams : lanes);
+    if (streams > nchunks) streams = nchunks;
     float h_exp[kExpTableSize];
     host_exp_table(h_exp);
     Temp d_exp, d_queue;
@@ -471,6 +573,7 @@ extern "C" int gw_sgns_train(int32_t n, int32_t d, const int32_t *tokens, int64_
     P.tokens = tokens; P.W = W; P.L = L; P.n = n; P.K = K; P.epochs = epochs; P.epoch = 0;
     P.alpha0 = alpha0; P.alpha_span = alpha0 - alpha_min; P.alpha_min = alpha_min;
     P.job_walks = job_walks; P.chunk_walks = chunk_walks;
+    P.streams = streams; P.stream_chunks = ceil_div<int64_t>(nchunks, streams);
     P.job_queue = d_queue.as<unsigned long long>();
     P.alias = alias_table; P.exp_table = d_exp.as<float>();
     P.syn0 = syn0; P.syn1neg = syn1neg; P.key0 = (uint32_t)seed; P.key1 = (uint32_t)(seed >> 32);

@@ -224,8 +224,9 @@ class DeepWalk(object):
         ``hs`` (0).  GPU-only knobs: ``lanes`` (number of concurrent workers, the analogue of
         gensim's ``workers``: each trains one 1000-walk job at a time, taken from a queue in corpus
         order; 0 = library default, 1 = sequential), ``chunk_walks`` (walks a worker takes from
-        the queue at a time; must divide the job size; 0 = library default) and ``sgns_seed``
-        (Philox key of the negative draws).
+        the queue at a time; must divide the job size; 0 = library default), ``streams`` (corpus
+        slices the queue deals chunks from in turn; 0 = library default) and ``sgns_seed`` (Philox
+        key of the negative draws).
         """
         import torch
         _lib.require_cuda()
@@ -238,6 +239,7 @@ class DeepWalk(object):
         hs = int(kwargs.pop('hs', 0))
         lanes = int(kwargs.pop('lanes', 0))
         chunk_walks = int(kwargs.pop('chunk_walks', 0))
+        streams = int(kwargs.pop('streams', 0))
         sgns_seed = kwargs.pop('sgns_seed', None)
         if kwargs:
             raise TypeError('word2vec() got unexpected keyword arguments %s' % sorted(kwargs))
@@ -256,7 +258,8 @@ class DeepWalk(object):
         dv = self.train_device(vector_size=vector_size, negative=negative, epochs=epochs,
                                alpha=alpha, min_alpha=min_alpha, init_seed=init_seed,
                                ns_exponent=ns_exponent, batch_words=batch_words,
-                               lanes=lanes, chunk_walks=chunk_walks, sgns_seed=sgns_seed)
+                               lanes=lanes, chunk_walks=chunk_walks, streams=streams,
+                               sgns_seed=sgns_seed)
         # results -> host (the only synchronisation of the replicate)
         nodes = dv['nodes']
         nv = int(dv['n_vocab'].item())
@@ -277,7 +280,7 @@ class DeepWalk(object):
         logger.info('Generating node vectors done in %.2fs' % (end - start))
 
     def train_device(self, vector_size=8, negative=5, epochs=5, alpha=0.025, min_alpha=0.0001,
-                     init_seed=1, ns_exponent=0.75, batch_words=10000, lanes=0, chunk_walks=0,
+                     init_seed=1, ns_exponent=0.75, batch_words=10000, lanes=0, chunk_walks=0, streams=0,
                      sgns_seed=None, epoch_hook=None):
         """Enqueue vocabulary, alias table, init and the SGNS epochs on the current stream and
         return the device tensors (no host synchronisation).  ``epoch_hook(ep, when)`` is called
@@ -313,27 +316,31 @@ class DeepWalk(object):
         _lib.call('gw_sgns_init', n, d, _lib.ptr(rank_of_node), _lib.ptr(rng_rows), _lib.ptr(syn0),
                   _lib.ptr(syn1neg), st)
         job_walks = max(1, int(batch_words) // max(L, 1))
-        if int(lanes) == 0 or int(chunk_walks) == 0:
+        if int(lanes) == 0 or int(chunk_walks) == 0 or int(streams) == 0:
             import ctypes
-            a_l, a_c = ctypes.c_int64(0), ctypes.c_int64(0)
-            _lib.call('gw_sgns_auto_shape', n, W, job_walks, ctypes.byref(a_l), ctypes.byref(a_c))
+            a_l, a_c, a_s = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
+            _lib.call('gw_sgns_auto_shape', n, W, job_walks, ctypes.byref(a_l), ctypes.byref(a_c),
+                      ctypes.byref(a_s))
             if int(lanes) == 0:
                 lanes = a_l.value
             if int(chunk_walks) == 0:
                 chunk_walks = job_walks if int(lanes) == 1 else a_c.value
+            if int(streams) == 0:
+                streams = 1 if int(lanes) == 1 else min(a_s.value, int(lanes))
         for ep in range(int(epochs)):
             if epoch_hook is not None:
                 epoch_hook(ep, 'before')
             _lib.call('gw_sgns_train', n, d, _lib.ptr(tokens), W, L, 1, int(negative), int(epochs),
                       ep, ep + 1, float(alpha), float(min_alpha), job_walks, int(chunk_walks),
-                      _lib.ptr(alias),
+                      int(streams), _lib.ptr(alias),
                       _lib.ptr(syn0), _lib.ptr(syn1neg), int(sgns_seed), int(lanes), st)
             if epoch_hook is not None:
                 epoch_hook(ep, 'after')
         return {'nodes': nodes, 'n': n, 'W': W, 'L': L, 'syn0': syn0, 'syn1neg': syn1neg,
                 'counts': counts, 'rank_of_node': rank_of_node, 'node_of_rank': node_of_rank,
                 'n_vocab': n_vocab, 'alias': alias, 'rng_rows': rng_rows,
-                'lanes': int(lanes), 'chunk_walks': int(chunk_walks), 'job_walks': job_walks,
+                'lanes': int(lanes), 'chunk_walks': int(chunk_walks), 'streams': int(streams),
+                'job_walks': job_walks,
                 'h2d_bytes': rows.nbytes}
 
 

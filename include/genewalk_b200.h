@@ -121,12 +121,15 @@ int gw_sgns_init(int32_t n, int32_t d, const int32_t *rank_of_node, const float 
  * alpha = max(alpha_min, alpha0 - (alpha0-alpha_min) * ((ep + j*job_walks/W) / epochs))
  * (gensim _get_next_alpha).  `lanes` workers (a worker = one group of d/2 <= 32 GPU threads; the
  * analogue of gensim's `workers`) take chunks of chunk_walks consecutive walks (chunk_walks divides
- * job_walks) from a queue in corpus order and train them concurrently, racing on the tables with
- * red.global.add (Hogwild).  lanes = 1 is the sequential statement of the algorithm (bit-exact
- * against the oracle); lanes = 0 / chunk_walks = 0 pick gw_sgns_auto_shape().
+ * job_walks) from a queue and train them concurrently, racing on the tables with red.global.add
+ * (Hogwild).  The queue deals chunks in corpus order from `streams` equal slices of the corpus in
+ * turn (streams = 1: plain corpus order), which bounds the number of workers that train walks
+ * starting at the same node at ~lanes/streams.  lanes = 1 is the sequential statement of the
+ * algorithm (bit-exact against the oracle); lanes / chunk_walks / streams = 0 pick
+ * gw_sgns_auto_shape().
  * Pair q = 2i + (j>i) of walk w draws its K negatives from Philox4x32-10(ctr {lo32(w), hi32(w),
  * (q<<4)|c, (ep<<8)|0x53}, key = seed): negative t uses words 2(t-1), 2(t-1)+1:
- * slot = mulhi32(x0, n), u = (x1>>8)*2^-24, target = u < prob[slot] ? slot : alias[slot];
+ * slot = mulhi32(x0, n), target = (x1>>16) < min(65535, floor(prob[slot]*2^16)) ? slot : alias[slot];
  * a draw equal to the centre is skipped.  Update rule = gensim w2v_fast_sentence_sg_neg, all
  * arithmetic unfused fp32; the dot product sums d/2 (<= 32) chunks left to right and combines the
  * chunk sums by a pairwise tree.  d in {8,16,32,64,128}; K <= 32; L <= 4096.
@@ -134,12 +137,12 @@ int gw_sgns_init(int32_t n, int32_t d, const int32_t *rank_of_node, const float 
 int gw_sgns_train(int32_t n, int32_t d, const int32_t *tokens, int64_t W, int32_t L,
                   int32_t window, int32_t K, int32_t epochs, int32_t epoch_begin,
                   int32_t epoch_end, double alpha0, double alpha_min, int64_t job_walks,
-                  int64_t chunk_walks, const gw_alias_entry *alias_table, float *syn0,
-                  float *syn1neg, uint64_t seed, int64_t lanes, gw_stream_t stream);
+                  int64_t chunk_walks, int64_t streams, const gw_alias_entry *alias_table,
+                  float *syn0, float *syn1neg, uint64_t seed, int64_t lanes, gw_stream_t stream);
 
-/* the (lanes, chunk_walks) gw_sgns_train uses when they are passed as 0 (host pointers) */
+/* the (lanes, chunk_walks, streams) gw_sgns_train uses when they are passed as 0 (host pointers) */
 int gw_sgns_auto_shape(int32_t n, int64_t W, int64_t job_walks, int64_t *lanes_out,
-                       int64_t *chunk_out);
+                       int64_t *chunk_out, int64_t *streams_out);
 
 /* ---- (4) similarity statistics ------------------------------------------------------------ */
 

@@ -218,8 +218,10 @@ static void pair_update(int sampler, draw_state *ds, int32_t V, int32_t d, int32
                 }
                 const uint32_t x0 = ds->rnd[w & 3], x1 = ds->rnd[(w & 3) + 1];
                 const int32_t slot = (int32_t)(((uint64_t)x0 * (uint32_t)V) >> 32);
-                const float u = (float)(x1 >> 8) * (1.0f / 16777216.0f);
-                target = (u < ds->alias_prob[slot]) ? slot : ds->alias_idx[slot];
+                /* 16-bit coin against the slot's acceptance threshold floor(prob * 2^16) (<= 65535) */
+                uint32_t thr = (uint32_t)floorf(ds->alias_prob[slot] * 65536.0f);
+                if (thr > 65535u) thr = 65535u;
+                target = ((x1 >> 16) < thr) ? slot : ds->alias_idx[slot];
             }
             if (target == centre) continue;
             label = 0.0f;
@@ -227,9 +229,12 @@ static void pair_update(int sampler, draw_state *ds, int32_t V, int32_t d, int32
         float *row2 = syn1neg + (int64_t)target * d;
         const float f = dot_rows(row1, row2, d);
         if (f <= -(float)GWO_MAX_EXP || f >= (float)GWO_MAX_EXP) continue;
-        const float sig =
-            exp_table[(int)((double)(f + (float)GWO_MAX_EXP) *
-                            ((double)GWO_EXP_TABLE_SIZE / (double)GWO_MAX_EXP / 2.0))];
+        /* for the largest floats below 6, f + 6 rounds up to 12.0f and gensim's index becomes 1000,
+         * one past its table (it then reads the adjacent static array); clamped to the last entry */
+        int ei = (int)((double)(f + (float)GWO_MAX_EXP) *
+                       ((double)GWO_EXP_TABLE_SIZE / (double)GWO_MAX_EXP / 2.0));
+        if (ei >= GWO_EXP_TABLE_SIZE) ei = GWO_EXP_TABLE_SIZE - 1;
+        const float sig = exp_table[ei];
         const float g = (label - sig) * alpha;
         for (int k = 0; k < d; ++k) work[k] = work[k] + g * row2[k];
         for (int k = 0; k < d; ++k) row2[k] = row2[k] + g * row1[k];

@@ -247,14 +247,14 @@ def sgns_case(n, m, niter, L, d, K, epochs, seed):
 
 
 def gpu_sgns(tok, n, d, K, epochs, prob, alias, syn0, syn1, seed, lanes, job_walks=1000,
-             alpha0=0.025, alpha_min=0.0001, chunk_walks=0):
+             alpha0=0.025, alpha_min=0.0001, chunk_walks=0, streams=0):
     L, W = tok.shape
     table = np.empty((n, 2), dtype=np.int32)
     table[:, 0] = prob.view(np.int32)
     table[:, 1] = alias
     d0, d1 = dev(syn0), dev(syn1)
     _lib.call('gw_sgns_train', n, d, _lib.ptr(dev(tok, np.int32)), W, L, 1, K, epochs, 0, epochs,
-              alpha0, alpha_min, job_walks, chunk_walks, _lib.ptr(dev(table)), _lib.ptr(d0), _lib.ptr(d1),
+              alpha0, alpha_min, job_walks, chunk_walks, streams, _lib.ptr(dev(table)), _lib.ptr(d0), _lib.ptr(d1),
               seed, lanes, st())
     torch.cuda.synchronize()
     return d0.cpu().numpy(), d1.cpu().numpy()
@@ -309,7 +309,8 @@ def test_sgns_hogwild_close_to_sequential():
     want0, want1 = syn0.copy(), syn1.copy()
     olib.sgns_train(tok, n, d, want0, want1, sampler=1, K=K, epochs=epochs, alias_prob=prob,
                     alias_idx=alias, seed=77)
-    got0, _ = gpu_sgns(tok, n, d, K, epochs, prob, alias, syn0, syn1, 77, lanes=16, chunk_walks=25)
+    got0, _ = gpu_sgns(tok, n, d, K, epochs, prob, alias, syn0, syn1, 77, lanes=16, chunk_walks=25,
+                       streams=2)
     assert np.isfinite(got0).all()
     row_ptr, col_idx = graphs.csr_arrays(n, 1500, seed=21, self_loops=2)
     s_want = stats_ref.null_similarities(row_ptr, col_idx, want0)
@@ -325,11 +326,12 @@ def test_sgns_chunk_must_divide_job():
 
 
 def test_sgns_auto_shape():
-    lanes, chunk = ctypes.c_int64(0), ctypes.c_int64(0)
+    lanes, chunk, streams = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
     for n, W in ((2300, 3465000), (38000, 152681600), (1000000, 1000000000), (3, 400)):
-        _lib.call('gw_sgns_auto_shape', n, W, 1000, ctypes.byref(lanes), ctypes.byref(chunk))
+        _lib.call('gw_sgns_auto_shape', n, W, 1000, ctypes.byref(lanes), ctypes.byref(chunk),
+                  ctypes.byref(streams))
         assert 1 <= lanes.value <= max(1, n // 2) and 1000 % chunk.value == 0
-        assert lanes.value * chunk.value <= max(W // 50, chunk.value)
+        assert 1 <= streams.value <= lanes.value and lanes.value <= 160 * streams.value or n < 6400
 
 
 # ------------------------------------------------------------------------------------------------

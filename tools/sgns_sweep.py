@@ -19,6 +19,7 @@ lanes_list = [int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else 
     [2048, 4096, 9472, 18944]
 chunk = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 stride = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+streams = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 n, u, v, is_go = graphs.human_scale_edges(seed=2, n_genes=int(20000 * scale), n_go=int(18000 * scale),
                                           n_gene_edges=int(700000 * scale), n_annot=int(250000 * scale),
                                           n_isa=int(50000 * scale), n_modules=max(4, int(500 * scale)))
@@ -37,12 +38,12 @@ for lanes in lanes_list:
         e = torch.cuda.Event(enable_timing=True)
         e.record()
         ev.append(e)
-    dv = dw.train_device(epochs=5, lanes=lanes, chunk_walks=chunk, epoch_hook=hook)
+    dv = dw.train_device(epochs=5, lanes=lanes, chunk_walks=chunk, streams=streams, epoch_hook=hook)
     torch.cuda.synchronize()
     ms = [ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(5)]
     ok = bool(torch.isfinite(dv['syn0']).all().item())
     out['lanes'][lanes] = {'ms_per_epoch': ms, 'pairs_per_s': pairs / (np.mean(ms[1:]) / 1e3),
                            'finite': ok}
-    print(lanes, ['%.1f' % m for m in ms], '%.3g pairs/s' % (pairs / (np.mean(ms[1:]) / 1e3)), ok,
+    print(lanes, dv['chunk_walks'], dv['streams'], ['%.1f' % m for m in ms], '%.3g pairs/s' % (pairs / (np.mean(ms[1:]) / 1e3)), ok,
           flush=True)
 print(json.dumps(out))
