@@ -32,22 +32,6 @@ constexpr float kMaxExp = 6.0f;
 constexpr int kTrainThreads = 512;      // upper bound of the CTA size (launch bounds)
 constexpr int kSmemAliasMaxN = 56000;   // 4 B/entry packed alias table + EXP_TABLE fit 227 KB
 
-#ifdef GW_DEBUG_BLOWUP
-__device__ unsigned long long g_dbg[16];
-__device__ __forceinline__ void dbg_record(int site, int a, int b, float x, float y, float z)
-{
-    if (atomicCAS(&g_dbg[0], 0ULL, 1ULL) == 0ULL) {
-        g_dbg[1] = (unsigned long long)site; g_dbg[2] = (unsigned long long)(unsigned)a;
-        g_dbg[3] = (unsigned long long)(unsigned)b; g_dbg[4] = (unsigned long long)__float_as_uint(x);
-        g_dbg[5] = (unsigned long long)__float_as_uint(y); g_dbg[6] = (unsigned long long)__float_as_uint(z);
-        g_dbg[7] = (unsigned long long)(blockIdx.x * blockDim.x + threadIdx.x);
-    }
-}
-#define GW_DBG(site, a, b, x, y, z) do { if (!(fabsf(x) < 1e4f) || !(fabsf(y) < 1e4f) || !(fabsf(z) < 1e4f)) dbg_record(site, a, b, x, y, z); } while (0)
-#else
-#define GW_DBG(site, a, b, x, y, z) do { } while (0)
-#endif
-
 struct TrainParams {
     const int32_t *tokens;
     int64_t W;
@@ -318,8 +302,6 @@ __device__ __forceinline__ void step_update(const TrainParams &P, const float *s
             }
             if (ft <= -kMaxExp || ft >= kMaxExp) continue;
             const float g = __fmul_rn(__fsub_rn(t == 0 ? 1.0f : 0.0f, s_exp[sigmoid_index(ft)]), alpha);
-            GW_DBG(100 + t + (o ? 10 : 0), c, tg[x], ft, g, row[0]);
-            GW_DBG(200 + t + (o ? 10 : 0), c, tg[x], ctx[0], ctx[1], row[1]);
             float delta[E];
 #pragma unroll
             for (int k = 0; k < E; ++k) {
@@ -492,17 +474,6 @@ static int64_t chunk_divisor(int64_t job_walks, int64_t want)
 // ~128 of them train walks that start at the same node; training keeps sweeping the corpus in the
 // reference's node-major order when few slices are active and the chunks in flight inside a slice
 // cover little more than one start node.  Within that: as many workers as fill the GPU.
-#ifdef GW_DEBUG_BLOWUP
-extern "C" int gw_debug_read(unsigned long long *out16)
-{
-    cudaDeviceSynchronize();
-    cudaMemcpyFromSymbol(out16, gw::g_dbg, sizeof(unsigned long long) * 16);
-    unsigned long long z[16] = {0};
-    cudaMemcpyToSymbol(gw::g_dbg, z, sizeof z);
-    return 0;
-}
-#endif
-
 extern "C" int gw_sgns_auto_shape(int32_t n, int64_t W, int64_t job_walks, int64_t *lanes_out,
                                   int64_t *chunk_out, int64_t *streams_out)
 {

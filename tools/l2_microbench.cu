@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256) bench_kernel(float *table, uint32_t n, in
         for (int u = 0; u < UNROLL; ++u) {
             const uint32_t r = lcg(s) >> 8;
             if (MODE == 3) rows[u] = zipf[r % zipf_n];
-            else if (MODE == 4) rows[u] = 0;
+            else if (MODE == 4 || MODE >= 10) rows[u] = 0;
             else rows[u] = r % n;
         }
         if (MODE == 0) {
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256) bench_kernel(float *table, uint32_t n, in
             }
         } else if (MODE >= 5) {
             // sub-warp cooperative access: G adjacent lanes share one row (one 32 B sector)
-            constexpr int G = (MODE == 5 || MODE == 6) ? 4 : (MODE == 7 || MODE == 8) ? 8 : 2;
+            constexpr int G = (MODE == 5 || MODE == 6 || MODE == 10) ? 4 : (MODE == 7 || MODE == 8 || MODE == 12) ? 8 : 2;
             const int sub = threadIdx.x & (G - 1);
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
@@ -67,8 +67,8 @@ __global__ void __launch_bounds__(256) bench_kernel(float *table, uint32_t n, in
                 float *p = table + (size_t)row * 8 + sub * (8 / G);
                 if (MODE == 5) { const float2 v = __ldcg(reinterpret_cast<const float2 *>(p)); acc += v.x + v.y; }
                 else if (MODE == 7) { acc += __ldcg(p); }
-                else if (MODE == 6) asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(1e-9f), "f"(1e-9f) : "memory");
-                else if (MODE == 8) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(1e-9f) : "memory");
+                else if (MODE == 6 || MODE == 10) asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(1e-9f), "f"(1e-9f) : "memory");
+                else if (MODE == 8 || MODE == 12) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(1e-9f) : "memory");
                 else red_add_v4(p, 1e-9f, 1e-9f, 1e-9f, 1e-9f);
             }
         } else {
@@ -96,7 +96,7 @@ static double run(float *table, uint32_t n, int blocks, int iters, const uint32_
     CK(cudaEventSynchronize(b));
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, a, b));
-    const int G = (MODE == 5 || MODE == 6) ? 4 : (MODE == 7 || MODE == 8) ? 8 : (MODE == 9) ? 2 : 1;
+    const int G = (MODE == 5 || MODE == 6 || MODE == 10) ? 4 : (MODE == 7 || MODE == 8 || MODE == 12) ? 8 : (MODE == 9 || MODE == 11) ? 2 : 1;
     const double rows = (double)blocks * 256 * iters * 6 / G;
     return rows / (ms * 1e-3);   // rows per second
 }
@@ -139,13 +139,17 @@ int main(int argc, char **argv)
         double g7 = run<7>(table, n, blocks, iters, dz, zn, sink);
         double r8 = run<8>(table, n, blocks, iters, dz, zn, sink);
         double r9 = run<9>(table, n, blocks, iters, dz, zn, sink);
+        double r10 = run<10>(table, n, blocks, iters / 8, dz, zn, sink);
+        double r11 = run<11>(table, n, blocks, iters / 8, dz, zn, sink);
+        double r12 = run<12>(table, n, blocks, iters / 8, dz, zn, sink);
         printf(", \"ctas_per_sm_%d\": {\"gather16x2_rows_per_s\": %.4g, \"gather16x2_GBps\": %.1f, "
                "\"gather32_rows_per_s\": %.4g, \"gather32_GBps\": %.1f, \"red16x2_rows_per_s\": %.4g, "
                "\"red16x2_GBps\": %.1f, \"red_zipf_rows_per_s\": %.4g, \"red_single_rows_per_s\": %.4g, "
                "\"gather_4lanes_x8B_rows_per_s\": %.4g, \"red_4lanes_v2_rows_per_s\": %.4g, "
                "\"gather_8lanes_x4B_rows_per_s\": %.4g, \"red_8lanes_f32_rows_per_s\": %.4g, "
-               "\"red_2lanes_v4_rows_per_s\": %.4g}",
-               occ[oi], g0, g0 * 32 / 1e9, g1, g1 * 32 / 1e9, r2, r2 * 32 / 1e9, r3, r4, g5, r6, g7, r8, r9);
+               "\"red_2lanes_v4_rows_per_s\": %.4g, \"red_single_4lanes_v2_rows_per_s\": %.4g, "
+               "\"red_single_2lanes_v4_rows_per_s\": %.4g, \"red_single_8lanes_f32_rows_per_s\": %.4g}",
+               occ[oi], g0, g0 * 32 / 1e9, g1, g1 * 32 / 1e9, r2, r2 * 32 / 1e9, r3, r4, g5, r6, g7, r8, r9, r10, r11, r12);
     }
     printf("}\n");
     return 0;
