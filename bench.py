@@ -73,6 +73,13 @@ class ClockMonitor(threading.Thread):
                 'samples': len(self.samples)}
 
 
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def build_inputs(scale):
     from tests import graphs
     ng, ngo = int(20000 * scale), int(18000 * scale)
@@ -116,7 +123,7 @@ def run_reference(args):
     graphs, n, u, v, is_go, ng = build_inputs(args.scale)
     row_ptr, col_idx = graphs.csr_from_edges_numpy(n, u, v)
     from oracle import lib as olib
-    threads = olib.lib().gwo_max_threads()
+    threads = host_threads()   # torchrun exports OMP_NUM_THREADS=1: ask the OS instead
     vals, sample = [], ''
     t_all = time.perf_counter()
     for i in range(args.warmup + args.steps):
@@ -301,10 +308,26 @@ def run_ours(args):
                 'sgns_kernel_pairs_per_s': pairs_launch / (k_avg / 1e3),
                 'sgns_shape': {'lanes': dv['lanes'], 'chunk_walks': dv['chunk_walks'], 'streams': dv['streams'],
                                'job_walks': dv['job_walks']}}
+    if args.pipeline > 0:
+        # BASELINE metric, first item: end-to-end seconds of node_vectors + null_distribution +
+        # statistics (cli.py:194-252) with nreps_graph = nreps_null = --pipeline, replicates sharded
+        from genewalk_b200.replicates import run_genewalk
+        barrier()
+        p0 = time.perf_counter()
+        df = run_genewalk(mg, genes, nreps_graph=args.pipeline, nreps_null=args.pipeline,
+                          alpha_fdr=0.1, gene_id_type='custom', base_seed=2024, lanes=args.lanes)
+        barrier()
+        t_p = torch.tensor([time.perf_counter() - p0], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(t_p, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            line['pipeline'] = {'nreps_graph': args.pipeline, 'nreps_null': args.pipeline,
+                                'seconds': float(t_p.item()), 'rows_significant': int(len(df)),
+                                'alpha_fdr': 0.1}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import lib as olib
         csr.to_host()
-        threads = olib.lib().gwo_max_threads()
+        threads = host_threads()
         rate, sample = cpu_sample_rate(csr.row_ptr, csr.col_idx, threads)
         line['cpu_baseline'] = {'value': rate, 'unit': 'pairs/s', 'cores': threads, 'kind': 'port',
                                 'sample': sample}
@@ -323,6 +346,8 @@ def main():
     ap.add_argument('--scale', type=float, default=1.0, help='shrink the workload (tests only)')
     ap.add_argument('--lanes', type=int, default=0, dest='lanes')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--pipeline', type=int, default=0,
+                    help='also time the full pipeline with this many real and null replicates')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours' and args.scale == 1.0:
         print('warning: fewer than 3 warm-up steps', file=sys.stderr)

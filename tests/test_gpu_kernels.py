@@ -277,6 +277,26 @@ def test_sgns_sequential_bit_exact(n, m, niter, L, d, K, epochs):
     assert np.array_equal(got1.view(np.uint32), want1.view(np.uint32))
 
 
+def test_sgns_large_vocabulary_bit_exact():
+    """n > 56000: the noise table stays in global memory (no shared-memory copy); same bits."""
+    n, d, K = 70000, 8, 5
+    row_ptr, col_idx = graphs.csr_arrays(n, 120000, seed=9, power_law=False)
+    tok = olib.walk_uniform(row_ptr, col_idx, 1, 10, 4, 0, 0, 3000)
+    counts = np.bincount(tok.ravel(), minlength=n)
+    prob, alias = olib.alias_table(counts)
+    syn0, syn1 = olib.gensim_init_weights(n, d, seed=1)
+    want0, want1 = syn0.copy(), syn1.copy()
+    olib.sgns_train(tok, n, d, want0, want1, sampler=1, K=K, epochs=2, alias_prob=prob,
+                    alias_idx=alias, seed=8)
+    got0, got1 = gpu_sgns(tok, n, d, K, 2, prob, alias, syn0, syn1, 8, lanes=1)
+    assert np.array_equal(got0, want0) and np.array_equal(got1, want1)
+    # and the concurrent run on the same input stays finite and close in distribution
+    got0c, _ = gpu_sgns(tok, n, d, K, 2, prob, alias, syn0, syn1, 8, lanes=64, chunk_walks=8, streams=1)
+    assert np.isfinite(got0c).all()
+    touched = counts > 0
+    assert np.abs(got0c[touched] - want0[touched]).mean() < 0.02
+
+
 def test_sgns_ragged_walks_bit_exact():
     n, d, K = 30, 8, 5
     tok, prob, alias, syn0, syn1 = sgns_case(n, 90, 2, 10, d, K, 1, seed=3)
