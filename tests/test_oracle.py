@@ -258,24 +258,23 @@ def _ring_of_cliques():
 
 
 def test_sgns_oracle_learns_structure_both_samplers():
-    """Both negative samplers (gensim cum_table+LCG in corpus order; Philox+alias in permuted
-    order) train embeddings in which neighbours are more similar than non-neighbours, and their
-    neighbour-similarity distributions agree (KS)."""
+    """Both negative samplers (gensim cum_table+LCG; Philox+alias), on the same corpus in the
+    reference's order, train embeddings in which neighbours are more similar than non-neighbours,
+    and their neighbour-similarity distributions agree (KS)."""
     from scipy.stats import ks_2samp
     csr = _ring_of_cliques()
     n = csr.n
     sims = {}
     for mode in ('gensim', 'device'):
         acc = []
-        for seed in range(4):
+        for seed in range(6):
             if mode == 'gensim':
                 tok = olib.walk_uniform(csr.row_ptr, csr.col_idx, 100, 10, seed, 0)
                 itn, syn0, _ = olib.word2vec_gensim_like(tok, n)
                 vec = np.zeros((n, 8), np.float32)
                 vec[itn] = syn0
             else:
-                tok = olib.walk_uniform(csr.row_ptr, csr.col_idx, 100, 10, seed,
-                                        coprime_stride(csr.nnz))
+                tok = olib.walk_uniform(csr.row_ptr, csr.col_idx, 100, 10, seed, 0)
                 counts = np.bincount(tok.ravel(), minlength=n)
                 prob, alias = olib.alias_table(counts)
                 vec, syn1 = olib.gensim_init_weights(n, 8)
@@ -286,7 +285,7 @@ def test_sgns_oracle_learns_structure_both_samplers():
             allp = stats_ref.cosine_similarity(vec, a, b)
             assert acc[-1].mean() > allp.mean() + 0.2
         sims[mode] = np.concatenate(acc)
-    assert ks_2samp(sims['gensim'], sims['device']).statistic < 0.12
+    assert ks_2samp(sims['gensim'], sims['device']).statistic < 0.1
 
 
 def test_sgns_oracle_threads_smoke():
