@@ -181,7 +181,8 @@ def test_embedding_recovers_planted_structure():
     a, b = rng.integers(0, len(wv), 5000), rng.integers(0, len(wv), 5000)
     rnd = stats_ref.cosine_similarity(wv.vectors, a, b)
     assert np.isfinite(wv.vectors).all()
-    assert nbr.mean() > rnd.mean() + 0.25
+    # the sequential gensim-faithful oracle gives 0.62 vs 0.34 on this network
+    assert nbr.mean() > rnd.mean() + 0.15 and 0.5 < nbr.mean() < 0.75
 
 
 # ---- null model ------------------------------------------------------------------------------------
