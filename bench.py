@@ -264,6 +264,13 @@ def run_ours(args):
     except Exception:
         pass
 
+    l2_peaks = {}
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'l2_pattern_peaks.json')) as f:
+            l2_peaks = json.load(f)
+    except Exception:
+        pass
+
     # ---- e2e: public API with host inputs ---------------------------------------------------
     barrier()
     h2d = csr.row_ptr.nbytes + csr.col_idx.nbytes + n * D * 4
@@ -303,6 +310,14 @@ def run_ours(args):
                              'pairs_per_launch': pairs_launch, 'avg_launch_ms': k_avg,
                              'note': 'tables are L2-resident by design: the algorithmic bytes are '
                                      'L2 sector traffic; HBM carries only the token stream'},
+                'roofline_l2': {
+                    'what': 'SGNS steps/s (2 pairs) vs the measured rate of the same gather+reduce '
+                            'pattern in isolation (tools/l2_mixbench.cu, profiles/l2_pattern_peaks.json)',
+                    'achieved_steps_per_s': pairs_launch / 2 / (k_avg / 1e3),
+                    'peak_uniform_rows': l2_peaks.get('uniform_rows'),
+                    'peak_c2_row_popularity': l2_peaks.get('c2_popularity'),
+                    'frac_of_uniform': (pairs_launch / 2 / (k_avg / 1e3) / l2_peaks['uniform_rows'])
+                    if l2_peaks.get('uniform_rows') else None},
                 'walk': {'steps_per_s': W * (WL - 1) / (walk_ms / 1e3), 'ms': walk_ms,
                          'achieved_gbs': BYTES_PER_STEP * W * (WL - 1) / (walk_ms / 1e3) / 1e9},
                 'sgns_kernel_pairs_per_s': pairs_launch / (k_avg / 1e3),
