@@ -470,7 +470,7 @@ static int64_t chunk_divisor(int64_t job_walks, int64_t want)
 }  // namespace gw
 
 // Default parallel shape.  Fidelity constraints (parity study, profiles/):
-// the Hogwild staleness per table row stays small when the workers stay below ~n/2 and at most
+// the Hogwild staleness per table row stays small when the workers stay below ~n/4 and at most
 // ~128 of them train walks that start at the same node; training keeps sweeping the corpus in the
 // reference's node-major order when few slices are active and the chunks in flight inside a slice
 // cover little more than one start node.  Within that: as many workers as fill the GPU.
@@ -481,7 +481,7 @@ extern "C" int gw_sgns_auto_shape(int32_t n, int64_t W, int64_t job_walks, int64
     GW_REQUIRE(n > 0 && W > 0 && job_walks > 0 && lanes_out && chunk_out && streams_out,
                "gw_sgns_auto_shape: bad arguments");
     int64_t lanes = (int64_t)num_sms() * 64;
-    if (lanes > n / 2) lanes = n / 2;
+    if (lanes > n / 4) lanes = n / 4;
     if (lanes < 1) lanes = 1;
     const int64_t chunk = chunk_divisor(job_walks, 8);
     const int64_t nchunks = ceil_div<int64_t>(W, chunk);

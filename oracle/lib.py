@@ -131,12 +131,23 @@ def gensim_vocab(tokens, n, corpus_order_first_seen=True):
     walk 1 ...).  Returns (index_to_node [V'], node_to_index [n] with -1 for absent, counts [V']).
     """
     tokens = np.asarray(tokens)
-    counts = np.bincount(tokens.ravel(), minlength=n).astype(np.int64)
+    counts = np.zeros(n, dtype=np.int64)
+    for row in tokens:      # row by row: no 8-byte copy of the whole corpus
+        counts += np.bincount(row[row >= 0], minlength=n)
     present = np.nonzero(counts)[0]
     if corpus_order_first_seen:
-        flat = tokens.T.ravel()                     # walk-major scan
-        _, first = np.unique(flat, return_index=True)   # sorted by node id -> first position
-        order = present[np.argsort(first, kind='stable')]   # nodes by first appearance
+        # first position of every node in the walk-major corpus scan (walk 0 tokens 0..L-1, walk 1,
+        # ...), found chunk by chunk from the end (a later assignment overwrites an earlier one)
+        L, W = tokens.shape
+        first = np.full(n, np.iinfo(np.int64).max, dtype=np.int64)
+        step = max(1, (1 << 24) // max(L, 1))
+        for b in range(((W - 1) // step) * step, -1, -step):
+            e = min(W, b + step)
+            blk = np.ascontiguousarray(tokens[:, b:e].T).ravel()
+            pos = np.arange(b * L, e * L, dtype=np.int64)
+            ok = blk >= 0
+            first[blk[ok][::-1]] = pos[ok][::-1]
+        order = present[np.argsort(first[present], kind='stable')]   # nodes by first appearance
     else:
         order = present
     rank = np.argsort(-counts[order], kind='stable')
@@ -189,7 +200,9 @@ def word2vec_gensim_like(tokens, n, d=8, K=5, epochs=5, alpha0=0.025, alpha_min=
     sample=0) as genewalk/deepwalk.py:135-139 runs it.  Returns (index_to_node, vectors[V', d])."""
     index_to_node, node_to_index, counts = gensim_vocab(tokens, n)
     V = len(index_to_node)
-    tok_idx = node_to_index[np.asarray(tokens)].astype(np.int32)
+    tok_idx = np.empty(np.shape(tokens), dtype=np.int32)
+    for i, row in enumerate(np.asarray(tokens)):
+        tok_idx[i] = node_to_index[row]
     cum = gensim_cum_table(counts)
     syn0, syn1neg = gensim_init_weights(V, d, seed)
     W = tok_idx.shape[1]
