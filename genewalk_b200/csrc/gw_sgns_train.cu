@@ -480,7 +480,7 @@ extern "C" int gw_sgns_auto_shape(int32_t n, int64_t W, int64_t job_walks, int64
     using namespace gw;
     GW_REQUIRE(n > 0 && W > 0 && job_walks > 0 && lanes_out && chunk_out && streams_out,
                "gw_sgns_auto_shape: bad arguments");
-    int64_t lanes = (int64_t)num_sms() * 64;
+    int64_t lanes = (int64_t)num_sms() * 128;   // 1M-node graph: throughput saturates at ~128 workers/SM
     if (lanes > n / 4) lanes = n / 4;
     if (lanes < 1) lanes = 1;
     const int64_t chunk = chunk_divisor(job_walks, 8);
