@@ -59,7 +59,9 @@ struct TrainParams {
 template <int E> __device__ __forceinline__ void ld_slice(const float *p, float (&r)[E])
 {
     // L2 (never a stale L1 line: other SMs update these rows)
-    if constexpr (E == 2) {
+    if constexpr (E == 1) {
+        r[0] = __ldcg(p);
+    } else if constexpr (E == 2) {
         const float2 v = __ldcg(reinterpret_cast<const float2 *>(p));
         r[0] = v.x; r[1] = v.y;
     } else {
@@ -73,7 +75,9 @@ template <int E> __device__ __forceinline__ void ld_slice(const float *p, float 
 
 template <int E> __device__ __forceinline__ void red_slice(float *p, const float (&d)[E])
 {
-    if constexpr (E == 2) {
+    if constexpr (E == 1) {
+        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(d[0]) : "memory");
+    } else if constexpr (E == 2) {
         asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(d[0]), "f"(d[1]) : "memory");
     } else {
 #pragma unroll
