@@ -152,6 +152,23 @@ def main():
     spec['psim'] = {'sims': probe.tolist(), 'pvals': [GW.psim(s) for s in probe]}
     ls_in = [[0.5], [1e-16, 1e-16], [0.01, 0.02, 0.5], [1.0, 1.0, 1.0], [0.3, 1e-8, 0.9, 0.2]]
     spec['log_stats'] = {'vals': ls_in, 'out': [[float(x) for x in GW.log_stats(v)] for v in ls_in]}
+    # the other gene id types: same network, genes described the way gene_lists.py does
+    # (HGNC_SYMBOL / HGNC plus the species-specific id), first 25 genes + one gene not in the network
+    spec['id_types'] = {}
+    for id_type, extra in (('hgnc_symbol', None), ('hgnc_id', None), ('mgi_id', 'MGI'),
+                           ('rgd_id', 'RGD'), ('ensembl_id', 'ENSEMBL'), ('entrez_human', 'EGID')):
+        gl = []
+        for k, g in enumerate(genes[:25] + [{'ID': 'NOT_IN_GRAPH'}]):
+            d = {'HGNC_SYMBOL': g['ID'], 'HGNC': str(1000 + k)}
+            if extra:
+                d[extra] = '%s:%d' % (extra, 5000 + k)
+            gl.append(d)
+        GWt = ps.GeneWalk(mg, gl, nvs, null, gene_id_type=id_type)
+        dft = GWt.generate_output(alpha_fdr=1)
+        spec['id_types'][id_type] = {'genes': gl, 'columns': list(dft.columns),
+                                     'dtypes': [str(t) for t in dft.dtypes],
+                                     'records': json.loads(dft.to_json(orient='split',
+                                                                       double_precision=15))['data']}
     with open(os.path.join(HERE, 'statistics.json'), 'w') as f:
         json.dump(spec, f, indent=0)
     np.savez(os.path.join(HERE, 'statistics.npz'), null=null, **{'vec%d' % r: vecs[r] for r in range(3)})

@@ -269,6 +269,34 @@ def test_generate_output_matches_reference(alpha):
     assert sum(1 for a, b in zip(order[:-1], order[1:]) if a > b) <= len(order) // 50
 
 
+@pytest.mark.parametrize('id_type', ['hgnc_symbol', 'hgnc_id', 'mgi_id', 'rgd_id', 'ensembl_id',
+                                     'entrez_human'])
+def test_generate_output_other_id_types(id_type):
+    """Column layout and values for the non-custom gene id types (perform_statistics.py:127-145,
+    188-214, 226-243)."""
+    z = np.load(os.path.join(GOLD, 'statistics.npz'))
+    mg = load_graph(STAT['graph'])
+    nvs = [NodeVectors(STAT['keys'][r], z['vec%d' % r]) for r in range(3)]
+    want = STAT['id_types'][id_type]
+    gw = GeneWalk(mg, want['genes'], nvs, z['null'], gene_id_type=id_type)
+    df = gw.generate_output(alpha_fdr=1)
+    assert list(df.columns) == want['columns']
+    assert [str(t) for t in df.dtypes] == want['dtypes']
+    cols = want['columns']
+    got = json.loads(df.to_json(orient='split', double_precision=15))['data']
+    assert len(got) == len(want['records'])
+    key = lambda r: (r[cols.index('hgnc_symbol')], r[cols.index('go_id')] or '')   # noqa: E731
+    got_by = {key(r): r for r in got}
+    for w in want['records']:
+        g = got_by[key(w)]
+        for c, a, b in zip(cols, g, w):
+            if isinstance(b, float):
+                tol = 1e-5 if c in ('sim', 'sem_sim') else 1e-9
+                assert a == pytest.approx(b, rel=tol, abs=tol * 1e-3), (c, key(w))
+            else:
+                assert a == b, (c, key(w))
+
+
 def test_psim_and_log_stats_match_reference():
     gw, z = _golden_genewalk()
     for s, p in zip(STAT['psim']['sims'], STAT['psim']['pvals']):

@@ -264,7 +264,10 @@ def gpu_sgns(tok, n, d, K, epochs, prob, alias, syn0, syn1, seed, lanes, job_wal
                                                     (40, 120, 2, 10, 16, 5, 2),
                                                     (30, 90, 2, 7, 8, 3, 2),
                                                     (30, 90, 2, 5, 32, 2, 1),
-                                                    (25, 60, 2, 10, 16, 7, 1)])
+                                                    (25, 60, 2, 10, 16, 7, 1),
+                                                    (25, 60, 1, 6, 64, 5, 1),
+                                                    (25, 60, 1, 6, 128, 5, 1),
+                                                    (25, 60, 1, 6, 64, 3, 1)])
 def test_sgns_sequential_bit_exact(n, m, niter, L, d, K, epochs):
     tok, prob, alias, syn0, syn1 = sgns_case(n, m, niter, L, d, K, epochs, seed=7 + d)
     seed = 0xABCDEF01 + K
