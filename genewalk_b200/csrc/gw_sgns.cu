@@ -1,18 +1,11 @@
 // gw_sgns.cu -- vocabulary, noise (alias) table and weight init of the SGNS trainer; the training
 // kernel itself is in gw_sgns_train.cu.
-// Replaces gensim.models.Word2Vec(sg=1, window=1, negative=K, sample=0) as called at
-// /root/reference/genewalk/deepwalk.py:135-139 (gensim itself is third-party and absent from the
-// reference tree; the update rule below is its published w2v_fast_sentence_sg_neg).
-//
-// Layout / roofline.  syn0 and syn1neg are [n, d] fp32 row-major; at d = 8 a row is exactly one
-// 32-byte sector, and both tables (2*n*32 B = 2.4 MB at n = 38k, 64 MB at n = 1M) live in the
-// 126 MB L2 for the whole run, so the governing bound is L2 sector / reduction throughput, not HBM.
-// One THREAD owns one walk (18 (centre, context) pairs at L = 10) and, per pair, keeps the whole
-// context row, the K+1 target rows and the accumulated `work` row in registers: 2 + 2(K+1)
-// ld.global.cg.v4 (L1-bypassing: other SMs update these rows) and as many red.global.add.v4.f32
-// (one REDG.E.ADD.F32x4 per 16 bytes, fire-and-forget, no lost updates under Hogwild).
-// Algorithmic bytes per pair: 4d(2K+4) table + 8 token + 8K alias = 496 B at d=8, K=5.
-// The only HBM stream is the position-major token array (coalesced, read once per epoch).
+// Replaces the host-side steps of gensim.models.Word2Vec(sg=1, min_count=1, negative=K, sample=0)
+// as reached from /root/reference/genewalk/deepwalk.py:135-139 (gensim is third-party and absent
+// from the reference tree): build_vocab's counts and descending-count order, the count^0.75 noise
+// distribution (gensim: make_cum_table + bisect; here an alias table) and init_weights.
+// All of it is a few streaming passes over the token array and O(n) work on the vocabulary:
+// 0.05 % of a replicate.
 #include <math.h>
 
 #include "gw_common.cuh"
