@@ -3,18 +3,20 @@
 
     python bench.py --gpus N --steps K --warmup W [--impl reference] [--scale S]
 
-A "step" is ONE node_vectors replicate of the hot path on the human-scale synthetic gene-GO network
-(BASELINE.json configs[1]: ~20k genes + ~18k GO terms, ~1M edges; reference defaults
-walk_length=10, niter=100, vector_size=8, window=1, negative=5, epochs=5): random walks from every
-node (W = 100*A walks) followed by the 5 SGNS epochs over them (5 * 18 * W pairs).
-metric = SGNS (centre, context) pairs trained per second of whole-replicate time (walk generation,
+A "step" is the node_vectors stage at the reference's default nreps_graph = 3 (cli.py:200-214; flag
+--replicates) on the human-scale synthetic gene-GO network (BASELINE.json configs[1]: ~20k genes +
+~18k GO terms, ~1M edges; reference defaults walk_length=10, niter=100, vector_size=8, window=1,
+negative=5, epochs=5): per replicate, random walks from every node (W = 100*A walks) followed by
+the 5 SGNS epochs over them (5 * 18 * W pairs).  The replicates of a step are independent; they are
+enqueued on separate CUDA streams and train concurrently on the GPU.
+metric = SGNS (centre, context) pairs trained per second of whole-stage time (walk generation,
 vocabulary, alias table and init included).
 
   value   inputs (CSR) already resident in HBM, results left on the device
-  e2e     the same replicate through the public API run_walks(nx.MultiGraph): CSR extraction from
-          networkx, host->device copies, training, device->host copy of the vectors
-  N > 1   every rank runs its own replicate (the path shards by replicate); one NCCL
-          all-gather of the per-replicate gene-GO similarity vector closes each step (weak scaling)
+  e2e     the same stage through the public API run_walks_many(nx.MultiGraph, 3): CSR extraction
+          from networkx, host->device copies, training, device->host copy of the vectors
+  N > 1   every rank runs its own replicates (the path shards by replicate); one NCCL
+          all-gather of the per-replicate gene-GO similarity vectors closes each step (weak scaling)
   --impl reference   the reference's CPU path for the same step restated in C (oracle/, gensim-
           faithful SGNS, OpenMP Hogwild on all host cores) on a bounded sample of the same corpus
 """
@@ -34,7 +36,7 @@ sys.path.insert(0, ROOT)
 NITER, WL, D, K, EPOCHS = 100, 10, 8, 5, 5
 BYTES_PER_PAIR = 4 * D * (2 * K + 4) + 8 + 8 * K      # 496 at d=8, K=5
 BYTES_PER_STEP = 16                                     # walk step
-METRIC = 'SGNS pairs/s over a node_vectors replicate (walks + 5 SGNS epochs)'
+METRIC = 'SGNS pairs/s over the node_vectors stage (walks + 5 SGNS epochs per replicate)'
 
 
 # ---------------------------------------------------------------------------------------------
@@ -133,31 +135,32 @@ def run_reference(args):
             vals.append(rate)
     value = float(np.mean(vals))
     A = int(row_ptr[-1])
-    pairs_step = NITER * A * 2 * (WL - 1) * EPOCHS
+    pairs_step = args.replicates * NITER * A * 2 * (WL - 1) * EPOCHS
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'pairs/s',
             'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': 1e3 * pairs_step / value, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': workload_config(n, len(u), A, args.scale),
+            'config': workload_config(n, len(u), A, args.scale, args.replicates),
             'cpu_baseline': {'value': value, 'unit': 'pairs/s', 'cores': threads, 'kind': 'port',
                              'sample': sample},
             'e2e': {'value': value, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0,
                     'd2h_bytes_per_step': 0},
-            'note': 'ms_per_step is the full-replicate time extrapolated linearly from the sample; '
+            'note': 'ms_per_step is the full-stage time extrapolated linearly from the sample; '
                     'gensim is not installable here, the C oracle restates it (oracle/gw_oracle.c)',
             'wall_s': time.perf_counter() - t_all}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n, n_edges, A, scale):
-    return {'workload': 'human-scale synthetic gene-GO network, node_vectors replicate '
-                        '(BASELINE.json configs[1])',
-            'nodes': n, 'edges': n_edges, 'adjacency_entries': A, 'walks': NITER * A,
+def workload_config(n, n_edges, A, scale, reps):
+    return {'workload': 'human-scale synthetic gene-GO network, node_vectors stage of %d replicates '
+                        '(BASELINE.json configs[1], reference default nreps_graph=3)' % reps,
+            'nodes': n, 'edges': n_edges, 'adjacency_entries': A, 'walks_per_replicate': NITER * A,
+            'replicates_per_step': reps,
             'walk_length': WL, 'niter': NITER, 'vector_size': D, 'window': 1, 'negative': K,
-            'epochs': EPOCHS, 'pairs_per_step': NITER * A * 2 * (WL - 1) * EPOCHS,
+            'epochs': EPOCHS, 'pairs_per_step': reps * NITER * A * 2 * (WL - 1) * EPOCHS,
             'scale': scale,
-            'l2': 'token stream (%.1f GB) >> 126 MB L2; embedding tables are rebuilt every step'
-                  % (NITER * A * WL * 4 / 1e9)}
+            'l2': 'token streams (%.1f GB per replicate) >> 126 MB L2; embedding tables are rebuilt '
+                  'every step' % (NITER * A * WL * 4 / 1e9)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -166,7 +169,8 @@ def run_ours(args):
     import torch.distributed as dist
     from genewalk_b200 import _lib
     from genewalk_b200.csr import GraphCSR
-    from genewalk_b200.deepwalk import DeepWalk, run_walks
+    from genewalk_b200.deepwalk import DeepWalk
+    from genewalk_b200.replicates import run_walks_many
     from genewalk_b200.perform_statistics import GeneWalk
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -187,37 +191,50 @@ def run_ours(args):
     csr = GraphCSR.from_networkx(mg).to_device()
     A = csr.nnz
     W = NITER * A
-    pairs_step = W * 2 * (WL - 1) * EPOCHS
+    R = max(1, int(args.replicates))
+    pairs_step = R * W * 2 * (WL - 1) * EPOCHS
     gw = GeneWalk(mg, genes, [], np.zeros(1, np.float32), gene_id_type='custom')
     pairs = gw.collect_pairs()
     d_pg = torch.from_numpy(pairs['pair_gene'].astype(np.int32)).cuda()
     d_po = torch.from_numpy(pairs['pair_go'].astype(np.int32)).cuda()
     m_pairs = int(d_po.numel())
-    gathered = [torch.empty(m_pairs, dtype=torch.float32, device='cuda') for _ in range(world)]
-    st = _lib.stream_ptr()
-    train_events = []
-
-    def hook(ep, when):
-        e = torch.cuda.Event(enable_timing=True)
-        e.record()
-        train_events.append((ep, when, e))
+    gathered = [torch.empty((R, m_pairs), dtype=torch.float32, device='cuda') for _ in range(world)]
+    sims_all = torch.empty((R, m_pairs), dtype=torch.float32, device='cuda')
+    cur = torch.cuda.current_stream()
+    side = [torch.cuda.Stream() for _ in range(R)] if R > 1 else [cur]
+    train_events, walk_events = [], []
 
     def device_step(step, timed):
-        seed = (1 + step) * 1000003 + rank
-        dw = DeepWalk(csr, WL, NITER, seed=seed)
-        w0 = torch.cuda.Event(enable_timing=True); w1 = torch.cuda.Event(enable_timing=True)
-        w0.record()
-        dw.get_walks()
-        w1.record()
-        dv = dw.train_device(vector_size=D, negative=K, epochs=EPOCHS, lanes=args.lanes,
-                             epoch_hook=hook if timed else None)
-        # the replicate's product in the pipeline: gene-GO similarities (fixed length), exchanged
-        sims = torch.empty(m_pairs, dtype=torch.float32, device='cuda')
-        _lib.call('gw_cosine_pairs', D, _lib.ptr(dv['syn0']), m_pairs, _lib.ptr(d_pg),
-                  _lib.ptr(d_po), _lib.ptr(sims), st)
+        """R independent replicates, one per CUDA stream, then the exchange of their products."""
+        dvs = []
+        for k in range(R):
+            if R > 1:
+                side[k].wait_stream(cur)
+            with torch.cuda.stream(side[k]):
+                def hook(ep, when):
+                    e = torch.cuda.Event(enable_timing=True)
+                    e.record()
+                    train_events.append((len(dvs), ep, when, e))
+                seed = ((1 + step) * 1000003 + rank) * 16 + k
+                dw = DeepWalk(csr, WL, NITER, seed=seed)
+                w0 = torch.cuda.Event(enable_timing=True); w1 = torch.cuda.Event(enable_timing=True)
+                w0.record()
+                dw.get_walks()
+                w1.record()
+                if timed:
+                    walk_events.append((w0, w1))
+                dv = dw.train_device(vector_size=D, negative=K, epochs=EPOCHS, lanes=args.lanes,
+                                     shared_sm=R > 1, epoch_hook=hook if timed else None)
+                # the replicate's product in the pipeline: gene-GO similarities (fixed length)
+                _lib.call('gw_cosine_pairs', D, _lib.ptr(dv['syn0']), m_pairs, _lib.ptr(d_pg),
+                          _lib.ptr(d_po), _lib.ptr(sims_all[k]), _lib.stream_ptr())
+                dvs.append(dv)
+        if R > 1:
+            for k in range(R):
+                cur.wait_stream(side[k])
         if world > 1:
-            dist.all_gather(gathered, sims)
-        return (w0, w1), dv, sims
+            dist.all_gather(gathered, sims_all)
+        return dvs
 
     # ---- value: device-resident ------------------------------------------------------------
     for i in range(args.warmup):
@@ -228,10 +245,8 @@ def run_ours(args):
     launches0 = _lib.launch_count()
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
-    walk_ev = []
     for i in range(args.steps):
-        ev, dv, sims = device_step(args.warmup + i, True)
-        walk_ev.append(ev)
+        dv = device_step(args.warmup + i, True)[0]
     t1.record()
     barrier()
     launches = _lib.launch_count() - launches0
@@ -242,14 +257,24 @@ def run_ours(args):
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms_max = float(t_ms.item())
     value = world * pairs_step * args.steps / (ms_max / 1e3)
-    # dominant kernel: one SGNS epoch launch
-    befores = [e for ep, when, e in train_events if when == 'before']
-    afters = [e for ep, when, e in train_events if when == 'after']
+    # dominant kernel: one SGNS epoch launch.  With R > 1 the launches of different replicates
+    # overlap on the GPU, so the rate is (launches' pairs) / (time during which at least one SGNS
+    # launch was in flight), from the per-launch CUDA events on the launching streams.
+    befores = [e for _, ep, when, e in train_events if when == 'before']
+    afters = [e for _, ep, when, e in train_events if when == 'after']
     k_ms = [b.elapsed_time(a) for b, a in zip(befores, afters)]
     k_avg = float(np.mean(k_ms)) if k_ms else float('nan')
-    walk_ms = float(np.mean([a.elapsed_time(b) for a, b in walk_ev]))
+    spans = sorted((t0.elapsed_time(b), t0.elapsed_time(a)) for b, a in zip(befores, afters))
+    busy_ms, hi = 0.0, -1.0
+    for lo, up in spans:
+        if up > hi:
+            busy_ms += up - max(lo, hi)
+            hi = up
+    n_launch = len(spans)
+    walk_ms = float(np.mean([a.elapsed_time(b) for a, b in walk_events]))
     pairs_launch = W * 2 * (WL - 1)
-    achieved = BYTES_PER_PAIR * pairs_launch / (k_avg / 1e3) / 1e9
+    k_eff = busy_ms / max(n_launch, 1)            # GPU time per launch with the overlap credited
+    achieved = BYTES_PER_PAIR * pairs_launch / (k_eff / 1e3) / 1e9
     peaks = {}
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
@@ -273,18 +298,20 @@ def run_ours(args):
 
     # ---- e2e: public API with host inputs ---------------------------------------------------
     barrier()
-    h2d = csr.row_ptr.nbytes + csr.col_idx.nbytes + n * D * 4
     d2h = 0
+    h2d = csr.row_ptr.nbytes + csr.col_idx.nbytes + R * n * D * 4
     for i in range(min(args.warmup, 1)):
-        run_walks(mg, vector_size=D, walk_seed=7 + i, lanes=args.lanes)
+        run_walks_many(mg, R, base_seed=7 + i, concurrent=R, lanes=args.lanes)
     barrier()
     e0 = time.perf_counter()
     for i in range(args.steps):
-        dw = run_walks(mg, vector_size=D, walk_seed=100 + i * world + rank,
-                       lanes=args.lanes)
-        wv = dw.model.wv
-        d2h = wv.vectors.nbytes + dw.model.syn1neg.nbytes + wv.counts.nbytes + wv.node_ids.nbytes
-        del dw
+        dws = run_walks_many(mg, R, base_seed=100 + i * world + rank, concurrent=R, lanes=args.lanes)
+        d2h = 0
+        for dw in dws:
+            wv = dw.model.wv
+            d2h += (wv.vectors.nbytes + dw.model.syn1neg.nbytes + wv.counts.nbytes +
+                    wv.node_ids.nbytes)
+        del dws
     barrier()
     e_s = time.perf_counter() - e0
     t_e = torch.tensor([e_s], dtype=torch.float64, device='cuda')
@@ -297,7 +324,7 @@ def run_ours(args):
         line = {'metric': METRIC, 'value': value, 'unit': 'pairs/s', 'n_gpus': world,
                 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_max / args.steps,
                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-                'data': 'synthetic', 'config': workload_config(n, len(u), A, args.scale),
+                'data': 'synthetic', 'config': workload_config(n, len(u), A, args.scale, R),
                 'clocks': clocks,
                 'e2e': {'value': e2e_value, 'unit': 'pairs/s', 'h2d_bytes_per_step': int(h2d),
                         'd2h_bytes_per_step': int(d2h), 'ms_per_step': 1e3 * float(t_e.item()) / args.steps},
@@ -307,20 +334,24 @@ def run_ours(args):
                              'frac': achieved / peak, 'traffic': traffic,
                              'peak_source': 'measured (MEASURED_PEAKS.json hbm_gbs)' if peaks else 'fallback',
                              'algorithmic_bytes_per_pair': BYTES_PER_PAIR,
-                             'pairs_per_launch': pairs_launch, 'avg_launch_ms': k_avg,
-                             'note': 'tables are L2-resident by design: the algorithmic bytes are '
-                                     'L2 sector traffic; HBM carries only the token stream'},
+                             'pairs_per_launch': pairs_launch, 'avg_launch_ms': k_eff,
+                             'launches': n_launch, 'concurrent_launches': R,
+                             'launch_ms_on_its_stream': k_avg, 'sgns_busy_ms': busy_ms,
+                             'note': 'avg_launch_ms = (time with >= 1 SGNS launch in flight) / '
+                                     'launches: the launches of the R replicates of a step overlap. '
+                                     'Tables are L2-resident by design: the algorithmic bytes are '
+                                     'L2 sector traffic; HBM carries only the token streams'},
                 'roofline_l2': {
                     'what': 'SGNS steps/s (2 pairs) vs the measured rate of the same gather+reduce '
                             'pattern in isolation (tools/l2_mixbench.cu, profiles/l2_pattern_peaks.json)',
-                    'achieved_steps_per_s': pairs_launch / 2 / (k_avg / 1e3),
+                    'achieved_steps_per_s': pairs_launch / 2 / (k_eff / 1e3),
                     'peak_uniform_rows': l2_peaks.get('uniform_rows'),
                     'peak_c2_row_popularity': l2_peaks.get('c2_popularity'),
-                    'frac_of_uniform': (pairs_launch / 2 / (k_avg / 1e3) / l2_peaks['uniform_rows'])
+                    'frac_of_uniform': (pairs_launch / 2 / (k_eff / 1e3) / l2_peaks['uniform_rows'])
                     if l2_peaks.get('uniform_rows') else None},
                 'walk': {'steps_per_s': W * (WL - 1) / (walk_ms / 1e3), 'ms': walk_ms,
                          'achieved_gbs': BYTES_PER_STEP * W * (WL - 1) / (walk_ms / 1e3) / 1e9},
-                'sgns_kernel_pairs_per_s': pairs_launch / (k_avg / 1e3),
+                'sgns_kernel_pairs_per_s': pairs_launch / (k_eff / 1e3),
                 'sgns_shape': {'lanes': dv['lanes'], 'chunk_walks': dv['chunk_walks'], 'streams': dv['streams'],
                                'job_walks': dv['job_walks']}}
     if args.pipeline > 0:
@@ -330,7 +361,8 @@ def run_ours(args):
         barrier()
         p0 = time.perf_counter()
         df = run_genewalk(mg, genes, nreps_graph=args.pipeline, nreps_null=args.pipeline,
-                          alpha_fdr=0.1, gene_id_type='custom', base_seed=2024, lanes=args.lanes)
+                          alpha_fdr=0.1, gene_id_type='custom', base_seed=2024, lanes=args.lanes,
+                          concurrent=R)
         barrier()
         t_p = torch.tensor([time.perf_counter() - p0], dtype=torch.float64, device='cuda')
         if world > 1:
@@ -360,6 +392,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--scale', type=float, default=1.0, help='shrink the workload (tests only)')
     ap.add_argument('--lanes', type=int, default=0, dest='lanes')
+    ap.add_argument('--replicates', type=int, default=3,
+                    help='replicates per step, trained concurrently (reference default nreps_graph)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--pipeline', type=int, default=0,
                     help='also time the full pipeline with this many real and null replicates')

@@ -47,6 +47,7 @@ struct TrainParams {
     int64_t chunk_walks;  // walks a worker takes from the queue at a time (divides job_walks)
     int64_t streams;      // corpus slices the queue deals chunks from in turn (see gw_sgns_train)
     int64_t stream_chunks;  // chunks per slice
+    int32_t shared_sm;      // leave the SMs' shared memory to other kernels (concurrent replicates)
     unsigned long long *job_queue;  // next job to hand out (device counter, zeroed per launch)
     const gw_alias_entry *alias;
     const float *exp_table;  // [1000] device copy of gensim's EXP_TABLE
@@ -432,7 +433,7 @@ static int launch_train(const TrainParams &P, int64_t lanes, cudaStream_t s)
 {
     // `lanes` workers of G threads each.  With the noise table in shared memory (n <= 56000) one
     // CTA per SM holds lanes/num_sms workers (<= 512 threads); otherwise 128-thread CTAs.
-    const bool smem_alias = KT > 0 && P.n <= kSmemAliasMaxN;
+    const bool smem_alias = KT > 0 && P.n <= kSmemAliasMaxN && !P.shared_sm;
     const int sms = num_sms();
     int block, blocks;
     if (lanes * G <= 32) {
@@ -504,7 +505,7 @@ extern "C" int gw_sgns_train(int32_t n, int32_t d, const int32_t *tokens, int64_
                              int32_t epoch_end, double alpha0, double alpha_min, int64_t job_walks,
                              int64_t chunk_walks, int64_t streams, const gw_alias_entry *alias_table,
                              float *syn0, float *syn1neg, uint64_t seed, int64_t lanes,
-                             gw_stream_t stream)
+                             int32_t shared_sm, gw_stream_t stream)
 {
     using namespace gw;
     cudaStream_t s = (cudaStream_t)stream;
@@ -549,6 +550,7 @@ extern "C" int gw_sgns_train(int32_t n, int32_t d, const int32_t *tokens, int64_
     P.alpha0 = alpha0; P.alpha_span = alpha0 - alpha_min; P.alpha_min = alpha_min;
     P.job_walks = job_walks; P.chunk_walks = chunk_walks;
     P.streams = streams; P.stream_chunks = ceil_div<int64_t>(nchunks, streams);
+    P.shared_sm = shared_sm;
     P.job_queue = d_queue.as<unsigned long long>();
     P.alias = alias_table; P.exp_table = d_exp.as<float>();
     P.syn0 = syn0; P.syn1neg = syn1neg; P.key0 = (uint32_t)seed; P.key1 = (uint32_t)(seed >> 32);

@@ -225,8 +225,11 @@ class DeepWalk(object):
         gensim's ``workers``: each trains one 1000-walk job at a time, taken from a queue in corpus
         order; 0 = library default, 1 = sequential), ``chunk_walks`` (walks a worker takes from
         the queue at a time; must divide the job size; 0 = library default), ``streams`` (corpus
-        slices the queue deals chunks from in turn; 0 = library default) and ``sgns_seed`` (Philox
-        key of the negative draws).
+        slices the queue deals chunks from in turn; 0 = library default), ``shared_sm`` (True when
+        several replicates are trained at once on different CUDA streams: the kernel then leaves
+        the SMs' shared memory free for the others), ``wait`` (False: only enqueue the training on
+        the current CUDA stream; ``finish_word2vec()`` then downloads the vectors) and ``sgns_seed``
+        (Philox key of the negative draws).
         """
         import torch
         _lib.require_cuda()
@@ -240,6 +243,8 @@ class DeepWalk(object):
         lanes = int(kwargs.pop('lanes', 0))
         chunk_walks = int(kwargs.pop('chunk_walks', 0))
         streams = int(kwargs.pop('streams', 0))
+        shared_sm = bool(kwargs.pop('shared_sm', False))
+        kwargs_async = not bool(kwargs.pop('wait', True))
         sgns_seed = kwargs.pop('sgns_seed', None)
         if kwargs:
             raise TypeError('word2vec() got unexpected keyword arguments %s' % sorted(kwargs))
@@ -255,12 +260,27 @@ class DeepWalk(object):
             raise ValueError('min_count>1 is not implemented; GeneWalk uses min_count=1')
         logger.info('Generating node vectors...')
         start = time.time()
-        dv = self.train_device(vector_size=vector_size, negative=negative, epochs=epochs,
-                               alpha=alpha, min_alpha=min_alpha, init_seed=init_seed,
-                               ns_exponent=ns_exponent, batch_words=batch_words,
-                               lanes=lanes, chunk_walks=chunk_walks, streams=streams,
-                               sgns_seed=sgns_seed)
-        # results -> host (the only synchronisation of the replicate)
+        self._w2v_args = dict(sg=1, vector_size=int(vector_size), window=window, min_count=min_count,
+                              negative=negative, sample=sample, epochs=epochs, alpha=alpha,
+                              min_alpha=min_alpha, seed=init_seed, ns_exponent=ns_exponent,
+                              workers=workers)
+        self._pending = self.train_device(vector_size=vector_size, negative=negative, epochs=epochs,
+                                          alpha=alpha, min_alpha=min_alpha, init_seed=init_seed,
+                                          ns_exponent=ns_exponent, batch_words=batch_words,
+                                          lanes=lanes, chunk_walks=chunk_walks, streams=streams,
+                                          shared_sm=shared_sm, sgns_seed=sgns_seed)
+        if kwargs_async:
+            return          # training is enqueued; finish_word2vec() downloads the vectors
+        self.finish_word2vec()
+        end = time.time()
+        self.timings['word2vec_s'] = end - start
+        logger.info('Generating node vectors done in %.2fs' % (end - start))
+
+    def finish_word2vec(self):
+        """Download the vectors of an enqueued training (``word2vec(..., wait=False)``) and set
+        ``self.model`` (the only host synchronisation of a replicate)."""
+        dv = self._pending
+        self._pending = None
         nodes = dv['nodes']
         nv = int(dv['n_vocab'].item())
         order = dv['node_of_rank'][:nv].long()
@@ -270,17 +290,11 @@ class DeepWalk(object):
         order_h = order.cpu().numpy()
         wv = NodeVectors([nodes[i] for i in order_h], vectors, counts=cnt)
         wv.node_ids = order_h.astype(np.int32)   # row r of wv.vectors is graph node node_ids[r]
-        self.model = Word2VecModel(wv, syn1neg=out_layer, sg=1, vector_size=int(vector_size),
-                                   window=window, min_count=min_count, negative=negative,
-                                   sample=sample, epochs=epochs, alpha=alpha, min_alpha=min_alpha,
-                                   seed=init_seed, ns_exponent=ns_exponent,
-                                   corpus_count=dv['W'], workers=workers)
-        end = time.time()
-        self.timings['word2vec_s'] = end - start
-        logger.info('Generating node vectors done in %.2fs' % (end - start))
+        self.model = Word2VecModel(wv, syn1neg=out_layer, corpus_count=dv['W'], **self._w2v_args)
+        return self.model
 
     def train_device(self, vector_size=8, negative=5, epochs=5, alpha=0.025, min_alpha=0.0001,
-                     init_seed=1, ns_exponent=0.75, batch_words=10000, lanes=0, chunk_walks=0, streams=0,
+                     init_seed=1, ns_exponent=0.75, batch_words=10000, lanes=0, chunk_walks=0, streams=0, shared_sm=False,
                      sgns_seed=None, epoch_hook=None):
         """Enqueue vocabulary, alias table, init and the SGNS epochs on the current stream and
         return the device tensors (no host synchronisation).  ``epoch_hook(ep, when)`` is called
@@ -333,7 +347,8 @@ class DeepWalk(object):
             _lib.call('gw_sgns_train', n, d, _lib.ptr(tokens), W, L, 1, int(negative), int(epochs),
                       ep, ep + 1, float(alpha), float(min_alpha), job_walks, int(chunk_walks),
                       int(streams), _lib.ptr(alias),
-                      _lib.ptr(syn0), _lib.ptr(syn1neg), int(sgns_seed), int(lanes), st)
+                      _lib.ptr(syn0), _lib.ptr(syn1neg), int(sgns_seed), int(lanes),
+                      1 if shared_sm else 0, st)
             if epoch_hook is not None:
                 epoch_hook(ep, 'after')
         return {'nodes': nodes, 'n': n, 'W': W, 'L': L, 'syn0': syn0, 'syn1neg': syn1neg,

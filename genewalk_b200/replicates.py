@@ -131,38 +131,93 @@ def exchange_results(local_sims, local_null, nreps_graph, nreps_null, m, device,
 # ---------------------------------------------------------------------------------------------
 # the replicate bodies
 # ---------------------------------------------------------------------------------------------
-def real_replicate(csr, base_seed, rep, dim_rep=8, walk_length=10, niter=100, **w2v):
-    """cli.py:202-203: run_walks(MG.graph, workers, vector_size) -> DeepWalk (model.wv on host)."""
+DEFAULT_CONCURRENT = 3   # replicates trained at once per GPU (independent tables: see DESIGN 4.2)
+
+
+def real_replicate(csr, base_seed, rep, dim_rep=8, walk_length=10, niter=100, wait=True, **w2v):
+    """cli.py:202-203: run_walks(MG.graph, workers, vector_size) -> DeepWalk.  wait=False only
+    enqueues the work on the current CUDA stream; ``dw.finish_word2vec()`` completes it."""
     dw = DeepWalk(csr, walk_length, niter, seed=mix_seed(base_seed, 0, rep))
     dw.get_walks()
-    dw.word2vec(vector_size=dim_rep, sgns_seed=mix_seed(base_seed, 1, rep), **w2v)
+    dw.word2vec(vector_size=dim_rep, sgns_seed=mix_seed(base_seed, 1, rep), wait=wait, **w2v)
     return dw
 
 
-def null_replicate(mg_or_degrees, base_seed, rep, dim_rep=8, walk_length=10, niter=100, **w2v):
+class _NullJob(object):
+    """A null replicate in flight: randomized graph, walks and training enqueued on a stream."""
+
+    def __init__(self, mg, base_seed, rep, dim_rep, walk_length, niter, w2v):
+        import torch
+        self.dim_rep = dim_rep
+        self.rg = get_rand_graph(mg, seed=mix_seed(base_seed, 2, rep), materialize=False)
+        self.dw = DeepWalk(self.rg, walk_length, niter, seed=mix_seed(base_seed, 3, rep))
+        self.dw.get_walks()
+        self.dv = None
+        if len(self.dw.walks) > 0:
+            self.dv = self.dw.train_device(vector_size=dim_rep, sgns_seed=mix_seed(base_seed, 4, rep),
+                                           **w2v)
+        self.stream = torch.cuda.current_stream()
+
+    def finish(self):
+        """Null similarities (device float32 tensor), cli.py:235 / null_distributions.py:33-48."""
+        import ctypes
+        import torch
+        if self.dv is None:
+            return torch.zeros(0, dtype=torch.float32, device='cuda')
+        with torch.cuda.stream(self.stream):
+            csr = self.rg.csr
+            sims = torch.empty(csr.nnz, dtype=torch.float32, device=self.dv['syn0'].device)
+            cnt = ctypes.c_int64(0)
+            _lib.call('gw_null_similarities', csr.n, _lib.ptr(csr.d_row_ptr), _lib.ptr(csr.d_col_idx),
+                      int(self.dim_rep), _lib.ptr(self.dv['syn0']), _lib.ptr(sims), ctypes.byref(cnt),
+                      _lib.stream_ptr())
+            out = sims[:cnt.value].clone()
+        self.dv = None
+        return out
+
+
+def null_replicate(mg, base_seed, rep, dim_rep=8, walk_length=10, niter=100, **w2v):
     """cli.py:221-235: get_rand_graph -> run_walks -> get_null_distributions, all on the device.
     Returns (device float32 tensor of null similarities, DeepWalk)."""
-    import ctypes
+    job = _NullJob(mg, base_seed, rep, dim_rep, walk_length, niter, w2v)
+    return job.finish(), job.dw
+
+
+def run_walks_many(graph, n_replicates, base_seed=None, concurrent=DEFAULT_CONCURRENT,
+                   walk_length=10, niter=100, vector_size=8, **w2v):
+    """``[run_walks(graph, ...) for _ in range(n_replicates)]`` (cli.py:200-203) with up to
+    ``concurrent`` replicates trained at once on separate CUDA streams.  Returns the DeepWalk
+    objects (``.model.wv`` set)."""
     import torch
-    rg = get_rand_graph(mg_or_degrees, seed=mix_seed(base_seed, 2, rep), materialize=False)
-    dw = DeepWalk(rg, walk_length, niter, seed=mix_seed(base_seed, 3, rep))
-    dw.get_walks()
-    if len(dw.walks) == 0:
-        return torch.zeros(0, dtype=torch.float32, device='cuda'), dw
-    dv = dw.train_device(vector_size=dim_rep, sgns_seed=mix_seed(base_seed, 4, rep), **w2v)
-    csr = rg.csr
-    sims = torch.empty(csr.nnz, dtype=torch.float32, device=dv['syn0'].device)
-    cnt = ctypes.c_int64(0)
-    _lib.call('gw_null_similarities', csr.n, _lib.ptr(csr.d_row_ptr), _lib.ptr(csr.d_col_idx),
-              int(dim_rep), _lib.ptr(dv['syn0']), _lib.ptr(sims), ctypes.byref(cnt), _lib.stream_ptr())
-    return sims[:cnt.value], dw
+    _lib.require_cuda()
+    if base_seed is None:
+        base_seed = random.getrandbits(64)
+    csr = GraphCSR.from_networkx(graph).to_device() if not isinstance(graph, GraphCSR) else graph.to_device()
+    out = []
+    cur = torch.cuda.current_stream()
+    streams = [torch.cuda.Stream() for _ in range(max(1, min(concurrent, n_replicates)))]
+    for g0 in range(0, n_replicates, len(streams)):
+        group = []
+        for k, rep in enumerate(range(g0, min(n_replicates, g0 + len(streams)))):
+            streams[k].wait_stream(cur)
+            with torch.cuda.stream(streams[k]):
+                group.append((k, real_replicate(csr, base_seed, rep, vector_size, walk_length, niter,
+                                                wait=False, shared_sm=len(streams) > 1, **w2v)))
+        for k, dw in group:
+            with torch.cuda.stream(streams[k]):
+                dw.finish_word2vec()
+            cur.wait_stream(streams[k])
+            out.append(dw)
+    return out
 
 
 def run_genewalk(mg, genes, nreps_graph=3, nreps_null=3, alpha_fdr=1, gene_id_type='hgnc_symbol',
-                 dim_rep=8, base_seed=None, group=None, return_parts=False, **w2v):
+                 dim_rep=8, base_seed=None, group=None, return_parts=False,
+                 concurrent=DEFAULT_CONCURRENT, **w2v):
     """node_vectors + null_distribution + statistics stages of cli.run_main (cli.py:194-252) for an
     assembled ``nx.MultiGraph``; replicates are sharded over the ranks of the initialised process
-    group (one process per GPU).  Returns the results DataFrame (identical on every rank)."""
+    group (one process per GPU) and, on every GPU, up to ``concurrent`` of them are trained at once
+    on separate CUDA streams.  Returns the results DataFrame (identical on every rank)."""
     import torch
     _lib.require_cuda()
     ws, rank = world()
@@ -177,15 +232,35 @@ def run_genewalk(mg, genes, nreps_graph=3, nreps_null=3, alpha_fdr=1, gene_id_ty
     pairs = gw.collect_pairs()
     m = len(pairs['pair_go'])
     local_sims, local_null, nvs = {}, {}, {}
-    for kind, rep in plan_units(nreps_graph, nreps_null, ws, rank):
-        if kind == KIND_REAL:
-            logger.info('real replicate %d/%d on rank %d' % (rep + 1, nreps_graph, rank))
-            dw = real_replicate(csr, base_seed, rep, dim_rep, **w2v)
-            nvs[rep] = dw.model.wv
-            local_sims[rep] = gw.pair_similarities(dw.model.wv, pairs)
-        else:
-            logger.info('null replicate %d/%d on rank %d' % (rep + 1, nreps_null, rank))
-            local_null[rep], _ = null_replicate(mg, base_seed, rep, dim_rep, **w2v)
+    units = plan_units(nreps_graph, nreps_null, ws, rank)
+    cur = torch.cuda.current_stream()
+    nstreams = max(1, min(int(concurrent), len(units)))
+    streams = [torch.cuda.Stream() for _ in range(nstreams)]
+    shared = nstreams > 1
+    for g0 in range(0, len(units), nstreams):
+        jobs = []
+        for k, (kind, rep) in enumerate(units[g0:g0 + nstreams]):
+            streams[k].wait_stream(cur)
+            with torch.cuda.stream(streams[k]):
+                if kind == KIND_REAL:
+                    logger.info('real replicate %d/%d on rank %d' % (rep + 1, nreps_graph, rank))
+                    jobs.append((k, kind, rep, real_replicate(csr, base_seed, rep, dim_rep, wait=False,
+                                                              shared_sm=shared, **w2v)))
+                else:
+                    logger.info('null replicate %d/%d on rank %d' % (rep + 1, nreps_null, rank))
+                    jobs.append((k, kind, rep, _NullJob(mg, base_seed, rep, dim_rep, 10, 100,
+                                                        dict(shared_sm=shared, **w2v))))
+        for k, kind, rep, job in jobs:
+            with torch.cuda.stream(streams[k]):
+                if kind == KIND_REAL:
+                    job.finish_word2vec()
+                    nvs[rep] = job.model.wv
+                    local_sims[rep] = gw.pair_similarities(job.model.wv, pairs)
+                    job.walks = []            # release the token array
+                else:
+                    local_null[rep] = job.finish()
+                    job.dw.walks = []
+            cur.wait_stream(streams[k])
     dev = torch.device('cuda')
     sims, nulls = exchange_results(local_sims, local_null, nreps_graph, nreps_null, m, dev, group)
     pooled = torch.cat(nulls) if nulls else torch.zeros(0, dtype=torch.float32, device=dev)

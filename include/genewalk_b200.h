@@ -133,12 +133,17 @@ int gw_sgns_init(int32_t n, int32_t d, const int32_t *rank_of_node, const float 
  * a draw equal to the centre is skipped.  Update rule = gensim w2v_fast_sentence_sg_neg, all
  * arithmetic unfused fp32; the dot product sums d/2 (<= 32) chunks left to right and combines the
  * chunk sums by a pairwise tree.  d in {8,16,32,64,128}; K <= 32; L <= 4096.
- * A negative token ends its walk early (ragged corpora are padded with -1). */
+ * A negative token ends its walk early (ragged corpora are padded with -1).
+ * shared_sm != 0: the kernel keeps the noise table in global memory (L1/L2) instead of copying it
+ * into ~150 KB of shared memory per CTA, so that kernels of other replicates, launched on other
+ * streams, can run on the same SMs (independent replicates have independent tables: training
+ * several at once relieves the same-row reduction contention in L2). */
 int gw_sgns_train(int32_t n, int32_t d, const int32_t *tokens, int64_t W, int32_t L,
                   int32_t window, int32_t K, int32_t epochs, int32_t epoch_begin,
                   int32_t epoch_end, double alpha0, double alpha_min, int64_t job_walks,
                   int64_t chunk_walks, int64_t streams, const gw_alias_entry *alias_table,
-                  float *syn0, float *syn1neg, uint64_t seed, int64_t lanes, gw_stream_t stream);
+                  float *syn0, float *syn1neg, uint64_t seed, int64_t lanes, int32_t shared_sm,
+                  gw_stream_t stream);
 
 /* the (lanes, chunk_walks, streams) gw_sgns_train uses when they are passed as 0 (host pointers) */
 int gw_sgns_auto_shape(int32_t n, int64_t W, int64_t job_walks, int64_t *lanes_out,

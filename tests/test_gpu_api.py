@@ -357,3 +357,48 @@ def test_null_distribution_parity_with_gensim_faithful_oracle():
     # two independent reference runs differ by KS ~0.02-0.09 (profiles/parity_study_r01.md)
     assert ks_2samp(got, want).statistic < 0.1
     assert abs(got.mean() - want.mean()) < 0.05
+
+
+# ---- concurrent replicates (several trained at once on separate CUDA streams) ---------------------------
+def test_word2vec_enqueue_then_finish():
+    """word2vec(wait=False) only enqueues; finish_word2vec() yields the model of a blocking call."""
+    mg, _ = graphs.modular_gene_go_network(120, 30, 4, 500, 300, 40, seed=3)
+    a = DeepWalk(mg, 10, 20, seed=5)
+    a.get_walks()
+    a.word2vec(lanes=1, sgns_seed=9)
+    b = DeepWalk(mg, 10, 20, seed=5)
+    b.get_walks()
+    assert b.word2vec(lanes=1, sgns_seed=9, wait=False, shared_sm=True) is None
+    assert b.model is None
+    b.finish_word2vec()
+    assert b.model.wv.index_to_key == a.model.wv.index_to_key
+    assert np.array_equal(b.model.wv.vectors, a.model.wv.vectors)   # sequential mode is bit-exact
+
+
+def test_run_walks_many_equals_serial_replicates():
+    """Replicates trained at once on different streams are the replicates trained one by one
+    (sequential SGNS mode: bit-exact), and distinct replicates differ."""
+    from genewalk_b200.replicates import run_walks_many
+    mg, _ = graphs.modular_gene_go_network(150, 40, 5, 700, 400, 50, seed=8)
+    conc = run_walks_many(mg, 4, base_seed=21, concurrent=3, niter=20, lanes=1)
+    ser = run_walks_many(mg, 4, base_seed=21, concurrent=1, niter=20, lanes=1)
+    assert len(conc) == len(ser) == 4
+    for c, s in zip(conc, ser):
+        assert np.array_equal(np.asarray(c.walks.tokens.cpu()), np.asarray(s.walks.tokens.cpu()))
+        assert c.model.wv.index_to_key == s.model.wv.index_to_key
+        assert np.array_equal(c.model.wv.vectors, s.model.wv.vectors)
+    assert not np.array_equal(conc[0].model.wv.vectors, conc[1].model.wv.vectors)
+
+
+def test_run_genewalk_concurrency_does_not_change_inputs_or_statistics():
+    """run_genewalk(concurrent=3) vs concurrent=1 at lanes=1: identical similarities, null
+    distribution and table."""
+    from genewalk_b200.replicates import run_genewalk
+    mg, genes = graphs.modular_gene_go_network(120, 30, 4, 500, 300, 40, seed=13)
+    kw = dict(nreps_graph=2, nreps_null=3, alpha_fdr=1, gene_id_type='custom', base_seed=3,
+              return_parts=True, lanes=1)
+    d1, p1 = run_genewalk(mg, genes, concurrent=1, **kw)
+    d3, p3 = run_genewalk(mg, genes, concurrent=3, **kw)
+    assert np.array_equal(p1['sims'].cpu().numpy(), p3['sims'].cpu().numpy())
+    assert np.array_equal(p1['null'], p3['null'])
+    assert d1.equals(d3)

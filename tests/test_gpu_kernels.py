@@ -247,7 +247,7 @@ def sgns_case(n, m, niter, L, d, K, epochs, seed):
 
 
 def gpu_sgns(tok, n, d, K, epochs, prob, alias, syn0, syn1, seed, lanes, job_walks=1000,
-             alpha0=0.025, alpha_min=0.0001, chunk_walks=0, streams=0):
+             alpha0=0.025, alpha_min=0.0001, chunk_walks=0, streams=0, shared_sm=0):
     L, W = tok.shape
     table = np.empty((n, 2), dtype=np.int32)
     table[:, 0] = prob.view(np.int32)
@@ -255,7 +255,7 @@ def gpu_sgns(tok, n, d, K, epochs, prob, alias, syn0, syn1, seed, lanes, job_wal
     d0, d1 = dev(syn0), dev(syn1)
     _lib.call('gw_sgns_train', n, d, _lib.ptr(dev(tok, np.int32)), W, L, 1, K, epochs, 0, epochs,
               alpha0, alpha_min, job_walks, chunk_walks, streams, _lib.ptr(dev(table)), _lib.ptr(d0), _lib.ptr(d1),
-              seed, lanes, st())
+              seed, lanes, shared_sm, st())
     torch.cuda.synchronize()
     return d0.cpu().numpy(), d1.cpu().numpy()
 
@@ -274,10 +274,11 @@ def test_sgns_sequential_bit_exact(n, m, niter, L, d, K, epochs):
     want0, want1 = syn0.copy(), syn1.copy()
     olib.sgns_train(tok, n, d, want0, want1, sampler=1, K=K, epochs=epochs, job_walks=100,
                     alias_prob=prob, alias_idx=alias, seed=seed)
-    got0, got1 = gpu_sgns(tok, n, d, K, epochs, prob, alias, syn0, syn1, seed, lanes=1,
-                          job_walks=100)
-    assert np.array_equal(got0.view(np.uint32), want0.view(np.uint32))
-    assert np.array_equal(got1.view(np.uint32), want1.view(np.uint32))
+    for shared_sm in (0, 1):     # noise table in shared memory / in global memory: same bits
+        got0, got1 = gpu_sgns(tok, n, d, K, epochs, prob, alias, syn0, syn1, seed, lanes=1,
+                              job_walks=100, shared_sm=shared_sm)
+        assert np.array_equal(got0.view(np.uint32), want0.view(np.uint32))
+        assert np.array_equal(got1.view(np.uint32), want1.view(np.uint32))
 
 
 def test_sgns_large_vocabulary_bit_exact():
