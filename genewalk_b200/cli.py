@@ -24,8 +24,7 @@ import random
 
 import numpy as np
 
-from .deepwalk import run_walks
-from .null_distributions import get_rand_graph, get_null_distributions
+from .replicates import run_walks_many, null_replicates_many, DEFAULT_CONCURRENT
 from .perform_statistics import GeneWalk
 
 logger = logging.getLogger('genewalk.cli')
@@ -82,6 +81,8 @@ def build_parser():
     parser.add_argument('--dim_rep', default=8, type=int)
     parser.add_argument('--save_dw', default=False, type=bool)
     parser.add_argument('--random_seed', default=None, type=int)
+    parser.add_argument('--concurrent', default=DEFAULT_CONCURRENT, type=int,
+                        help='GPU build only: replicates trained at once on one GPU.')
     return parser
 
 
@@ -148,32 +149,40 @@ def run_main(args):
             genes, graph = _load_inputs(args, project_folder)
             save_pickle(genes, project_folder, 'genes')
             save_pickle(graph, project_folder, 'multi_graph')
-            for i in range(args.nreps_graph):
-                logger.info('%s/%s' % (i + 1, args.nreps_graph))
-                DW = run_walks(graph, workers=args.nproc, vector_size=args.dim_rep)
-                if args.save_dw:
-                    save_pickle(DW, project_folder, 'deepwalk_%d' % (i + 1))
-                nv = copy.deepcopy(DW.model.wv)
-                save_pickle(nv, project_folder, 'deepwalk_node_vectors_%d' % (i + 1))
-                del DW, nv
+            # cli.py:200-214; the replicates are independent and trained `--concurrent` at a time
+            step = max(1, args.concurrent)
+            for i0 in range(0, args.nreps_graph, step):
+                cnt = min(step, args.nreps_graph - i0)
+                logger.info('%s-%s/%s' % (i0 + 1, i0 + cnt, args.nreps_graph))
+                DWs = run_walks_many(graph, cnt, concurrent=step, vector_size=args.dim_rep,
+                                     workers=args.nproc)
+                for i, DW in enumerate(DWs, start=i0):
+                    if args.save_dw:
+                        save_pickle(DW, project_folder, 'deepwalk_%d' % (i + 1))
+                    nv = copy.deepcopy(DW.model.wv)
+                    save_pickle(nv, project_folder, 'deepwalk_node_vectors_%d' % (i + 1))
+                del DWs
                 gc.collect()
 
         if args.stage in ('all', 'null_distribution'):
             MG = load_pickle(project_folder, 'multi_graph')
             srd = []
-            for i in range(args.nreps_null):
-                logger.info('%s/%s' % (i + 1, args.nreps_null))
-                RG = get_rand_graph(MG, materialize=False)
-                DW = run_walks(RG, workers=args.nproc, vector_size=args.dim_rep)
-                if args.save_dw:
-                    save_pickle(DW, project_folder, 'deepwalk_rand_%d' % (i + 1))
-                nv = copy.deepcopy(DW.model.wv)
-                save_pickle(nv, project_folder, 'deepwalk_node_vectors_rand_%d' % (i + 1))
-                del DW
+            step = max(1, args.concurrent)
+            for i0 in range(0, args.nreps_null, step):   # cli.py:219-236
+                cnt = min(step, args.nreps_null - i0)
+                logger.info('%s-%s/%s' % (i0 + 1, i0 + cnt, args.nreps_null))
+                done = null_replicates_many(MG, cnt, concurrent=step, vector_size=args.dim_rep,
+                                            workers=args.nproc)
+                for i, (DW, sims) in enumerate(done, start=i0):
+                    if args.save_dw:
+                        save_pickle(DW, project_folder, 'deepwalk_rand_%d' % (i + 1))
+                    if DW.model is not None:
+                        save_pickle(copy.deepcopy(DW.model.wv), project_folder,
+                                    'deepwalk_node_vectors_rand_%d' % (i + 1))
+                    srd.append(sims)
+                del done
                 gc.collect()
-                srd += get_null_distributions(RG, nv)
-                del nv
-                gc.collect()
+            srd = np.concatenate(srd) if srd else np.zeros(0, np.float32)
             srd = np.sort(np.asarray(srd, dtype=np.float32))   # == np.asarray(sorted(srd)), cli.py:238
             save_pickle(srd, project_folder, 'genewalk_rand_simdists')
 

@@ -147,6 +147,7 @@ class DeepWalk(object):
         self.wl = walk_length
         self.niter = niter
         self.model = None
+        self._pending = None
         self.seed = seed
         self._csr = None
         self.timings = {}

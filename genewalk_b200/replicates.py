@@ -152,27 +152,30 @@ class _NullJob(object):
         self.rg = get_rand_graph(mg, seed=mix_seed(base_seed, 2, rep), materialize=False)
         self.dw = DeepWalk(self.rg, walk_length, niter, seed=mix_seed(base_seed, 3, rep))
         self.dw.get_walks()
-        self.dv = None
         if len(self.dw.walks) > 0:
-            self.dv = self.dw.train_device(vector_size=dim_rep, sgns_seed=mix_seed(base_seed, 4, rep),
-                                           **w2v)
+            self.dw.word2vec(vector_size=dim_rep, sgns_seed=mix_seed(base_seed, 4, rep), wait=False,
+                             **w2v)
         self.stream = torch.cuda.current_stream()
 
-    def finish(self):
-        """Null similarities (device float32 tensor), cli.py:235 / null_distributions.py:33-48."""
+    def finish(self, keep_model=False):
+        """Null similarities (device float32 tensor), cli.py:235 / null_distributions.py:33-48;
+        keep_model=True also downloads the vectors into ``self.dw.model``."""
         import ctypes
         import torch
-        if self.dv is None:
+        dv = getattr(self.dw, '_pending', None)
+        if dv is None:
             return torch.zeros(0, dtype=torch.float32, device='cuda')
         with torch.cuda.stream(self.stream):
             csr = self.rg.csr
-            sims = torch.empty(csr.nnz, dtype=torch.float32, device=self.dv['syn0'].device)
+            sims = torch.empty(csr.nnz, dtype=torch.float32, device=dv['syn0'].device)
             cnt = ctypes.c_int64(0)
             _lib.call('gw_null_similarities', csr.n, _lib.ptr(csr.d_row_ptr), _lib.ptr(csr.d_col_idx),
-                      int(self.dim_rep), _lib.ptr(self.dv['syn0']), _lib.ptr(sims), ctypes.byref(cnt),
+                      int(self.dim_rep), _lib.ptr(dv['syn0']), _lib.ptr(sims), ctypes.byref(cnt),
                       _lib.stream_ptr())
             out = sims[:cnt.value].clone()
-        self.dv = None
+            if keep_model:
+                self.dw.finish_word2vec()
+        self.dw._pending = None
         return out
 
 
@@ -208,6 +211,32 @@ def run_walks_many(graph, n_replicates, base_seed=None, concurrent=DEFAULT_CONCU
                 dw.finish_word2vec()
             cur.wait_stream(streams[k])
             out.append(dw)
+    return out
+
+
+def null_replicates_many(mg, n_replicates, base_seed=None, concurrent=DEFAULT_CONCURRENT,
+                         walk_length=10, niter=100, vector_size=8, keep_model=True, **w2v):
+    """The body of the null_distribution loop (cli.py:219-236) for ``n_replicates`` randomized
+    networks, up to ``concurrent`` at once: ``[(DeepWalk, null similarities as numpy float32)]``."""
+    import torch
+    _lib.require_cuda()
+    if base_seed is None:
+        base_seed = random.getrandbits(64)
+    out = []
+    cur = torch.cuda.current_stream()
+    streams = [torch.cuda.Stream() for _ in range(max(1, min(concurrent, n_replicates)))]
+    for g0 in range(0, n_replicates, len(streams)):
+        jobs = []
+        for k, rep in enumerate(range(g0, min(n_replicates, g0 + len(streams)))):
+            streams[k].wait_stream(cur)
+            with torch.cuda.stream(streams[k]):
+                jobs.append((k, _NullJob(mg, base_seed, rep, vector_size, walk_length, niter,
+                                         dict(shared_sm=len(streams) > 1, **w2v))))
+        for k, job in jobs:
+            with torch.cuda.stream(streams[k]):
+                sims = job.finish(keep_model=keep_model).cpu().numpy()
+            cur.wait_stream(streams[k])
+            out.append((job.dw, sims))
     return out
 
 
