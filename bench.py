@@ -3,8 +3,9 @@
 
     python bench.py --gpus N --steps K --warmup W [--impl reference] [--scale S]
 
-A "step" is the node_vectors stage at the reference's default nreps_graph = 3 (cli.py:200-214; flag
---replicates) on the human-scale synthetic gene-GO network (BASELINE.json configs[1]: ~20k genes +
+A "step" is one batch of 6 node_vectors replicates (cli.py:200-214; flag --replicates) -- the batch
+the replicate driver trains at once per GPU; a default GeneWalk run holds 3 + 3 independent
+trainings, the nreps=10 run of BASELINE's metric 10 + 10 -- on the human-scale synthetic gene-GO network (BASELINE.json configs[1]: ~20k genes +
 ~18k GO terms, ~1M edges; reference defaults walk_length=10, niter=100, vector_size=8, window=1,
 negative=5, epochs=5): per replicate, random walks from every node (W = 100*A walks) followed by
 the 5 SGNS epochs over them (5 * 18 * W pairs).  The replicates of a step are independent; they are
@@ -13,7 +14,7 @@ metric = SGNS (centre, context) pairs trained per second of whole-stage time (wa
 vocabulary, alias table and init included).
 
   value   inputs (CSR) already resident in HBM, results left on the device
-  e2e     the same stage through the public API run_walks_many(nx.MultiGraph, 3): CSR extraction
+  e2e     the same batch through the public API run_walks_many(nx.MultiGraph, 6): CSR extraction
           from networkx, host->device copies, training, device->host copy of the vectors
   N > 1   every rank runs its own replicates (the path shards by replicate); one NCCL
           all-gather of the per-replicate gene-GO similarity vectors closes each step (weak scaling)
@@ -152,8 +153,8 @@ def run_reference(args):
 
 
 def workload_config(n, n_edges, A, scale, reps):
-    return {'workload': 'human-scale synthetic gene-GO network, node_vectors stage of %d replicates '
-                        '(BASELINE.json configs[1], reference default nreps_graph=3)' % reps,
+    return {'workload': 'human-scale synthetic gene-GO network, batch of %d node_vectors replicates '
+                        'trained concurrently (BASELINE.json configs[1])' % reps,
             'nodes': n, 'edges': n_edges, 'adjacency_entries': A, 'walks_per_replicate': NITER * A,
             'replicates_per_step': reps,
             'walk_length': WL, 'niter': NITER, 'vector_size': D, 'window': 1, 'negative': K,
@@ -224,7 +225,7 @@ def run_ours(args):
                 if timed:
                     walk_events.append((w0, w1))
                 dv = dw.train_device(vector_size=D, negative=K, epochs=EPOCHS, lanes=args.lanes,
-                                     shared_sm=R > 1, epoch_hook=hook if timed else None)
+                                     concurrent=R, epoch_hook=hook if timed else None)
                 # the replicate's product in the pipeline: gene-GO similarities (fixed length)
                 _lib.call('gw_cosine_pairs', D, _lib.ptr(dv['syn0']), m_pairs, _lib.ptr(d_pg),
                           _lib.ptr(d_po), _lib.ptr(sims_all[k]), _lib.stream_ptr())
@@ -392,8 +393,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--scale', type=float, default=1.0, help='shrink the workload (tests only)')
     ap.add_argument('--lanes', type=int, default=0, dest='lanes')
-    ap.add_argument('--replicates', type=int, default=3,
-                    help='replicates per step, trained concurrently (reference default nreps_graph)')
+    ap.add_argument('--replicates', type=int, default=6,
+                    help='replicates per step, trained concurrently on one GPU')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--pipeline', type=int, default=0,
                     help='also time the full pipeline with this many real and null replicates')

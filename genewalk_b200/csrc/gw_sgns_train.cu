@@ -48,6 +48,7 @@ struct TrainParams {
     int64_t streams;      // corpus slices the queue deals chunks from in turn (see gw_sgns_train)
     int64_t stream_chunks;  // chunks per slice
     int32_t shared_sm;      // leave the SMs' shared memory to other kernels (concurrent replicates)
+    int32_t merge;          // merged row reductions (Hogwild mode), see step_update_merged
     unsigned long long *job_queue;  // next job to hand out (device counter, zeroed per launch)
     const gw_alias_entry *alias;
     const float *exp_table;  // [1000] device copy of gensim's EXP_TABLE
@@ -327,7 +328,132 @@ __device__ __forceinline__ void step_update(const TrainParams &P, const float *s
     }
 }
 
-template <int D, int G, int KT, bool kSmemAlias>
+// ---- merged reductions (Hogwild mode) ------------------------------------------------------------
+// Over a walk every context row syn0[w_j] is the input of two pairs, (c = w_{j-1}, w_j) in step j-1
+// and (c = w_{j+1}, w_j) in step j+1, and the centre row syn1neg[w_j] is a target of both pairs of
+// step j.  These are the rows whose popularity is proportional to the node degree, i.e. the rows on
+// which the reductions of different workers meet in L2.  With other workers racing on the tables the
+// order in which ONE worker's own updates reach memory is immaterial, so in Hogwild mode a worker
+// holds the update of syn0[w_j] from step j-1 back (pending, in registers) and issues ONE reduction
+// with the sum of both updates in step j+1, and ONE reduction for the centre row per step: 13
+// gathers + 12 reductions per step instead of 13 + 14, the degree-proportional reductions halved.
+// Every row is still gathered fresh from L2 right before use (a view carried in registers over two
+// steps would miss the other workers' updates: measured, it costs as much fidelity as tripling the
+// worker count); the worker adds its own pending update to the fresh row, so its arithmetic sees
+// every one of its updates.  Run sequentially the result differs from the per-pair order only by
+// float summation order; the oracle restates this order too (gw_oracle.c:walk_merged, bit-exact).
+template <int E> struct CtxCarry {
+    float pX[E];           // update of syn0[walk[i-1]] not yet reduced into memory (from step i-2)
+    float pY[E];           // the same for syn0[walk[i]] (from step i-1, due in step i+1)
+    int32_t xn, yn;        // their nodes, -1 = nothing pending
+};
+
+template <int D, int G, int KT>
+__device__ __forceinline__ void step_update_merged(const TrainParams &P, const float *s_exp, int sub,
+                                                   unsigned gmask, int32_t c, int32_t a, int32_t b,
+                                                   float alpha, const int32_t (&tg)[2 * KT],
+                                                   StepRows<D, G, KT> &R, CtxCarry<D / G> &carry)
+{
+    constexpr int E = D / G;
+    const bool hasA = a >= 0, hasB = b >= 0;
+    const int64_t off = sub * E;
+    bool dup[2 * KT];
+#pragma unroll
+    for (int x = 0; x < 2 * KT; ++x) {
+        dup[x] = false;
+#pragma unroll
+        for (int y = 0; y < x; ++y) dup[x] |= (tg[y] == tg[x]);
+    }
+    float dC[E];
+    bool anyC = false;
+#pragma unroll
+    for (int k = 0; k < E; ++k) dC[k] = 0.0f;
+    // one pair against its K+1 targets; negatives are reduced at once, the centre's update is
+    // summed into dC (and into the register copy Rc, which the second pair reads)
+    auto pair = [&](float (&ctx)[E], float (&work)[E], const int o) {
+        float f[KT + 1];
+        f[0] = group_dot<E, G>(ctx, R.Rc, gmask);
+#pragma unroll
+        for (int k = 0; k < KT; ++k) f[k + 1] = group_dot<E, G>(ctx, R.N[o + k], gmask);
+#pragma unroll
+        for (int k = 0; k < E; ++k) work[k] = 0.0f;
+#pragma unroll
+        for (int t = 0; t <= KT; ++t) {
+            const int x = o + (t > 0 ? t - 1 : 0);
+            float *tp = P.syn1neg + (int64_t)(t == 0 ? c : tg[x]) * D + off;
+            float (&row)[E] = t == 0 ? R.Rc : R.N[x];
+            float ft = f[t];
+            if (t > 0) {
+                if (tg[x] == c) continue;
+                if (dup[x]) {
+                    ld_slice<E>(tp, row);
+                    ft = group_dot<E, G>(ctx, row, gmask);
+                }
+            }
+            if (ft <= -kMaxExp || ft >= kMaxExp) continue;
+            const float g = __fmul_rn(__fsub_rn(t == 0 ? 1.0f : 0.0f, s_exp[sigmoid_index(ft)]), alpha);
+            float delta[E];
+#pragma unroll
+            for (int k = 0; k < E; ++k) {
+                work[k] = __fadd_rn(work[k], __fmul_rn(g, row[k]));
+                delta[k] = __fmul_rn(g, ctx[k]);
+            }
+            if (t == 0) {
+#pragma unroll
+                for (int k = 0; k < E; ++k) {
+                    row[k] = __fadd_rn(row[k], delta[k]);
+                    dC[k] = __fadd_rn(dC[k], delta[k]);
+                }
+                anyC = true;
+            } else {
+                red_slice<E>(tp, delta);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < E; ++k) ctx[k] = __fadd_rn(ctx[k], work[k]);
+    };
+    float work[E];
+    if (hasA) {
+        const bool pending = carry.xn == a;
+        if (pending) {   // fresh row + this worker's own update still in registers
+#pragma unroll
+            for (int k = 0; k < E; ++k) R.Ra[k] = __fadd_rn(R.Ra[k], carry.pX[k]);
+        }
+        pair(R.Ra, work, 0);
+        if (pending) {
+#pragma unroll
+            for (int k = 0; k < E; ++k) work[k] = __fadd_rn(carry.pX[k], work[k]);
+        }
+        red_slice<E>(P.syn0 + (int64_t)a * D + off, work);
+    } else if (carry.xn >= 0) {
+        red_slice<E>(P.syn0 + (int64_t)carry.xn * D + off, carry.pX);   // not reachable in a walk
+    }
+    // the update of syn0[c] held back by the previous step is due in the next step
+#pragma unroll
+    for (int k = 0; k < E; ++k) carry.pX[k] = carry.pY[k];
+    carry.xn = carry.yn;
+    carry.yn = -1;
+    if (hasB) {
+        if (hasA && b == a) {   // the walk stepped back: continue on the updated row of pair A
+#pragma unroll
+            for (int k = 0; k < E; ++k) R.Rb[k] = R.Ra[k];
+        }
+        pair(R.Rb, carry.pY, KT);
+        carry.yn = b;
+    }
+    if (anyC) red_slice<E>(P.syn1neg + (int64_t)c * D + off, dC);
+}
+
+template <int D, int G>
+__device__ __forceinline__ void carry_flush(const TrainParams &P, int sub, CtxCarry<D / G> &carry)
+{
+    constexpr int E = D / G;
+    if (carry.xn >= 0) red_slice<E>(P.syn0 + (int64_t)carry.xn * D + sub * E, carry.pX);
+    if (carry.yn >= 0) red_slice<E>(P.syn0 + (int64_t)carry.yn * D + sub * E, carry.pY);
+    carry.xn = carry.yn = -1;
+}
+
+template <int D, int G, int KT, bool kSmemAlias, bool kMerge>
 __global__ void __launch_bounds__(kTrainThreads)
 sgns_train_kernel(const TrainParams P)
 {
@@ -376,6 +502,8 @@ sgns_train_kernel(const TrainParams P)
             if constexpr (KT > 0) {
                 StepDraw<G, KT, kSmemAlias> draw;
                 draw.issue(P, s_alias, sub, w_lo, w_hi, 0u);
+                CtxCarry<D / G> carry;
+                carry.xn = carry.yn = -1;
                 for (int32_t i = 0; i < P.L && cur >= 0; ++i) {
                     // token two positions ahead (the next step's right context), loaded early
                     const int32_t next2 = (i + 2 < P.L && next >= 0) ? __ldg(P.tokens + (int64_t)(i + 2) * P.W + w) : -1;
@@ -390,14 +518,22 @@ sgns_train_kernel(const TrainParams P)
                         for (int k = 0; k < KT; ++k) tg[KT + k] = cur;
                     }
                     StepRows<D, G, KT> rows;
-                    step_gather<D, G, KT>(P, sub, cur, prev, next, tg, rows);
-                    // the next step's draws (Philox + alias loads) overlap this step's row gathers
-                    draw.issue(P, s_alias, sub, w_lo, w_hi, 2u * (uint32_t)(i + 1));
-                    step_update<D, G, KT>(P, s_exp, sub, gmask, cur, prev, next, alpha, tg, rows);
+                    if constexpr (kMerge) {
+                        step_gather<D, G, KT>(P, sub, cur, prev, next, tg, rows);
+                        draw.issue(P, s_alias, sub, w_lo, w_hi, 2u * (uint32_t)(i + 1));
+                        step_update_merged<D, G, KT>(P, s_exp, sub, gmask, cur, prev, next, alpha, tg,
+                                                     rows, carry);
+                    } else {
+                        step_gather<D, G, KT>(P, sub, cur, prev, next, tg, rows);
+                        // the next step's draws (Philox + alias loads) overlap this step's row gathers
+                        draw.issue(P, s_alias, sub, w_lo, w_hi, 2u * (uint32_t)(i + 1));
+                        step_update<D, G, KT>(P, s_exp, sub, gmask, cur, prev, next, alpha, tg, rows);
+                    }
                     prev = cur;
                     cur = next;
                     next = next2;
                 }
+                if constexpr (kMerge) carry_flush<D, G>(P, sub, carry);
             } else {
                 for (int32_t i = 0; i < P.L && cur >= 0; ++i) {
                     int32_t neg[32];
@@ -451,12 +587,16 @@ static int launch_train(const TrainParams &P, int64_t lanes, cudaStream_t s)
     }
     size_t smem = sizeof(float) * kExpTableSize + (smem_alias ? sizeof(uint32_t) * (size_t)P.n : 0);
     GW_CUDA_OK(cudaMemsetAsync(P.job_queue, 0, sizeof(unsigned long long), s));
+    constexpr bool kCanMerge = KT > 0;
     if (smem_alias) {
-        GW_CUDA_OK(cudaFuncSetAttribute(sgns_train_kernel<D, G, KT, true>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        sgns_train_kernel<D, G, KT, true><<<blocks, block, smem, s>>>(P);
+        auto kern = (kCanMerge && P.merge) ? sgns_train_kernel<D, G, KT, true, kCanMerge>
+                                           : sgns_train_kernel<D, G, KT, true, false>;
+        GW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<blocks, block, smem, s>>>(P);
     } else {
-        sgns_train_kernel<D, G, KT, false><<<blocks, block, smem, s>>>(P);
+        auto kern = (kCanMerge && P.merge) ? sgns_train_kernel<D, G, KT, false, kCanMerge>
+                                           : sgns_train_kernel<D, G, KT, false, false>;
+        kern<<<blocks, block, smem, s>>>(P);
     }
     GW_LAUNCH_OK();
     return GW_OK;
@@ -479,13 +619,15 @@ static int64_t chunk_divisor(int64_t job_walks, int64_t want)
 // ~128 of them train walks that start at the same node; training keeps sweeping the corpus in the
 // reference's node-major order when few slices are active and the chunks in flight inside a slice
 // cover little more than one start node.  Within that: as many workers as fill the GPU.
-extern "C" int gw_sgns_auto_shape(int32_t n, int64_t W, int64_t job_walks, int64_t *lanes_out,
-                                  int64_t *chunk_out, int64_t *streams_out)
+extern "C" int gw_sgns_auto_shape(int32_t n, int64_t W, int64_t job_walks, int32_t concurrent,
+                                  int64_t *lanes_out, int64_t *chunk_out, int64_t *streams_out)
 {
     using namespace gw;
-    GW_REQUIRE(n > 0 && W > 0 && job_walks > 0 && lanes_out && chunk_out && streams_out,
+    GW_REQUIRE(n > 0 && W > 0 && job_walks > 0 && concurrent >= 1 && lanes_out && chunk_out && streams_out,
                "gw_sgns_auto_shape: bad arguments");
-    int64_t lanes = (int64_t)num_sms() * 128;   // 1M-node graph: throughput saturates at ~128 workers/SM
+    // 128 workers (512 threads at d = 8) per SM are resident at the kernel's register budget; the
+    // trainings that run at once share them (all co-resident: measured optimum)
+    int64_t lanes = (int64_t)num_sms() * 128 / concurrent;
     if (lanes > n / 4) lanes = n / 4;
     if (lanes < 1) lanes = 1;
     const int64_t chunk = chunk_divisor(job_walks, 8);
@@ -505,7 +647,7 @@ extern "C" int gw_sgns_train(int32_t n, int32_t d, const int32_t *tokens, int64_
                              int32_t epoch_end, double alpha0, double alpha_min, int64_t job_walks,
                              int64_t chunk_walks, int64_t streams, const gw_alias_entry *alias_table,
                              float *syn0, float *syn1neg, uint64_t seed, int64_t lanes,
-                             int32_t shared_sm, gw_stream_t stream)
+                             int32_t flags, gw_stream_t stream)
 {
     using namespace gw;
     cudaStream_t s = (cudaStream_t)stream;
@@ -531,7 +673,7 @@ extern "C" int gw_sgns_train(int32_t n, int32_t d, const int32_t *tokens, int64_
     GW_REQUIRE((reinterpret_cast<uintptr_t>(syn0) & 15) == 0 && (reinterpret_cast<uintptr_t>(syn1neg) & 15) == 0,
                "gw_sgns_train: tables must be 16-byte aligned");
     int64_t auto_lanes = 0, auto_chunk = 0, auto_streams = 0;
-    GW_TRY(gw_sgns_auto_shape(n, W, job_walks, &auto_lanes, &auto_chunk, &auto_streams));
+    GW_TRY(gw_sgns_auto_shape(n, W, job_walks, 1, &auto_lanes, &auto_chunk, &auto_streams));
     if (lanes == 0) lanes = auto_lanes;
     if (chunk_walks == 0) chunk_walks = lanes == 1 ? job_walks : auto_chunk;
     const int64_t nchunks = ceil_div<int64_t>(W, chunk_walks);
@@ -550,7 +692,9 @@ extern "C" int gw_sgns_train(int32_t n, int32_t d, const int32_t *tokens, int64_
     P.alpha0 = alpha0; P.alpha_span = alpha0 - alpha_min; P.alpha_min = alpha_min;
     P.job_walks = job_walks; P.chunk_walks = chunk_walks;
     P.streams = streams; P.stream_chunks = ceil_div<int64_t>(nchunks, streams);
-    P.shared_sm = shared_sm;
+    P.shared_sm = (flags & GW_SGNS_SHARED_SM) ? 1 : 0;
+    // per-pair reductions in gensim's order when sequential (bit-exact) or when asked for
+    P.merge = (flags & GW_SGNS_MERGED) ? 1 : (flags & GW_SGNS_PER_PAIR) ? 0 : (lanes > 1 ? 1 : 0);
     P.job_queue = d_queue.as<unsigned long long>();
     P.alias = alias_table; P.exp_table = d_exp.as<float>();
     P.syn0 = syn0; P.syn1neg = syn1neg; P.key0 = (uint32_t)seed; P.key1 = (uint32_t)(seed >> 32);

@@ -226,9 +226,10 @@ class DeepWalk(object):
         gensim's ``workers``: each trains one 1000-walk job at a time, taken from a queue in corpus
         order; 0 = library default, 1 = sequential), ``chunk_walks`` (walks a worker takes from
         the queue at a time; must divide the job size; 0 = library default), ``streams`` (corpus
-        slices the queue deals chunks from in turn; 0 = library default), ``shared_sm`` (True when
-        several replicates are trained at once on different CUDA streams: the kernel then leaves
-        the SMs' shared memory free for the others), ``wait`` (False: only enqueue the training on
+        slices the queue deals chunks from in turn; 0 = library default), ``concurrent`` (number of
+        trainings the caller runs at once on this GPU on different CUDA streams: they share the
+        GPU's resident workers and leave the SMs' shared memory to each other; default 1), ``reductions`` ('auto' | 'per_pair' | 'merged':
+        see ``gw_sgns_flags`` in include/genewalk_b200.h), ``wait`` (False: only enqueue the training on
         the current CUDA stream; ``finish_word2vec()`` then downloads the vectors) and ``sgns_seed``
         (Philox key of the negative draws).
         """
@@ -244,7 +245,9 @@ class DeepWalk(object):
         lanes = int(kwargs.pop('lanes', 0))
         chunk_walks = int(kwargs.pop('chunk_walks', 0))
         streams = int(kwargs.pop('streams', 0))
-        shared_sm = bool(kwargs.pop('shared_sm', False))
+        concurrent = int(kwargs.pop('concurrent', 1))
+        shared_sm = bool(kwargs.pop('shared_sm', concurrent > 1))
+        reductions = kwargs.pop('reductions', 'auto')
         kwargs_async = not bool(kwargs.pop('wait', True))
         sgns_seed = kwargs.pop('sgns_seed', None)
         if kwargs:
@@ -269,7 +272,8 @@ class DeepWalk(object):
                                           alpha=alpha, min_alpha=min_alpha, init_seed=init_seed,
                                           ns_exponent=ns_exponent, batch_words=batch_words,
                                           lanes=lanes, chunk_walks=chunk_walks, streams=streams,
-                                          shared_sm=shared_sm, sgns_seed=sgns_seed)
+                                          shared_sm=shared_sm, reductions=reductions, concurrent=concurrent,
+                                          sgns_seed=sgns_seed)
         if kwargs_async:
             return          # training is enqueued; finish_word2vec() downloads the vectors
         self.finish_word2vec()
@@ -295,8 +299,9 @@ class DeepWalk(object):
         return self.model
 
     def train_device(self, vector_size=8, negative=5, epochs=5, alpha=0.025, min_alpha=0.0001,
-                     init_seed=1, ns_exponent=0.75, batch_words=10000, lanes=0, chunk_walks=0, streams=0, shared_sm=False,
-                     sgns_seed=None, epoch_hook=None):
+                     init_seed=1, ns_exponent=0.75, batch_words=10000, lanes=0, chunk_walks=0,
+                     streams=0, shared_sm=None, reductions='auto', concurrent=1, sgns_seed=None,
+                     epoch_hook=None):
         """Enqueue vocabulary, alias table, init and the SGNS epochs on the current stream and
         return the device tensors (no host synchronisation).  ``epoch_hook(ep, when)`` is called
         with when in {'before', 'after'} around every epoch's launch (bench.py records CUDA
@@ -334,7 +339,8 @@ class DeepWalk(object):
         if int(lanes) == 0 or int(chunk_walks) == 0 or int(streams) == 0:
             import ctypes
             a_l, a_c, a_s = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
-            _lib.call('gw_sgns_auto_shape', n, W, job_walks, ctypes.byref(a_l), ctypes.byref(a_c),
+            _lib.call('gw_sgns_auto_shape', n, W, job_walks, max(1, int(concurrent)),
+                      ctypes.byref(a_l), ctypes.byref(a_c),
                       ctypes.byref(a_s))
             if int(lanes) == 0:
                 lanes = a_l.value
@@ -342,6 +348,9 @@ class DeepWalk(object):
                 chunk_walks = job_walks if int(lanes) == 1 else a_c.value
             if int(streams) == 0:
                 streams = 1 if int(lanes) == 1 else min(a_s.value, int(lanes))
+        if shared_sm is None:
+            shared_sm = int(concurrent) > 1
+        flags = (1 if shared_sm else 0) | {'auto': 0, 'per_pair': 2, 'merged': 4}[reductions]
         for ep in range(int(epochs)):
             if epoch_hook is not None:
                 epoch_hook(ep, 'before')
@@ -349,7 +358,7 @@ class DeepWalk(object):
                       ep, ep + 1, float(alpha), float(min_alpha), job_walks, int(chunk_walks),
                       int(streams), _lib.ptr(alias),
                       _lib.ptr(syn0), _lib.ptr(syn1neg), int(sgns_seed), int(lanes),
-                      1 if shared_sm else 0, st)
+                      flags, st)
             if epoch_hook is not None:
                 epoch_hook(ep, 'after')
         return {'nodes': nodes, 'n': n, 'W': W, 'L': L, 'syn0': syn0, 'syn1neg': syn1neg,

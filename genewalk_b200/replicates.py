@@ -131,7 +131,17 @@ def exchange_results(local_sims, local_null, nreps_graph, nreps_null, m, device,
 # ---------------------------------------------------------------------------------------------
 # the replicate bodies
 # ---------------------------------------------------------------------------------------------
-DEFAULT_CONCURRENT = 3   # replicates trained at once per GPU (independent tables: see DESIGN 4.2)
+DEFAULT_CONCURRENT = 6   # replicates trained at once per GPU (independent tables: see DESIGN 4.2)
+
+
+def fit_concurrent(requested, nnz, niter=100, walk_length=10):
+    """Replicates to run at once: ``requested``, capped so that their walk corpora (the only large
+    per-replicate allocation: niter * nnz walks of walk_length int32 tokens) fit the free HBM."""
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    free += torch.cuda.memory_reserved() - torch.cuda.memory_allocated()   # cached by the allocator
+    per_replicate = int(1.25 * 4 * walk_length * niter * max(int(nnz), 1)) + (256 << 20)
+    return max(1, min(int(requested), int(0.85 * free) // per_replicate))
 
 
 def real_replicate(csr, base_seed, rep, dim_rep=8, walk_length=10, niter=100, wait=True, **w2v):
@@ -198,6 +208,7 @@ def run_walks_many(graph, n_replicates, base_seed=None, concurrent=DEFAULT_CONCU
     csr = GraphCSR.from_networkx(graph).to_device() if not isinstance(graph, GraphCSR) else graph.to_device()
     out = []
     cur = torch.cuda.current_stream()
+    concurrent = fit_concurrent(concurrent, csr.nnz, niter, walk_length)
     streams = [torch.cuda.Stream() for _ in range(max(1, min(concurrent, n_replicates)))]
     for g0 in range(0, n_replicates, len(streams)):
         group = []
@@ -205,7 +216,7 @@ def run_walks_many(graph, n_replicates, base_seed=None, concurrent=DEFAULT_CONCU
             streams[k].wait_stream(cur)
             with torch.cuda.stream(streams[k]):
                 group.append((k, real_replicate(csr, base_seed, rep, vector_size, walk_length, niter,
-                                                wait=False, shared_sm=len(streams) > 1, **w2v)))
+                                                wait=False, concurrent=min(len(streams), n_replicates - g0), **w2v)))
         for k, dw in group:
             with torch.cuda.stream(streams[k]):
                 dw.finish_word2vec()
@@ -224,6 +235,7 @@ def null_replicates_many(mg, n_replicates, base_seed=None, concurrent=DEFAULT_CO
         base_seed = random.getrandbits(64)
     out = []
     cur = torch.cuda.current_stream()
+    concurrent = fit_concurrent(concurrent, sum(d for _, d in mg.degree()), niter, walk_length)
     streams = [torch.cuda.Stream() for _ in range(max(1, min(concurrent, n_replicates)))]
     for g0 in range(0, n_replicates, len(streams)):
         jobs = []
@@ -231,7 +243,7 @@ def null_replicates_many(mg, n_replicates, base_seed=None, concurrent=DEFAULT_CO
             streams[k].wait_stream(cur)
             with torch.cuda.stream(streams[k]):
                 jobs.append((k, _NullJob(mg, base_seed, rep, vector_size, walk_length, niter,
-                                         dict(shared_sm=len(streams) > 1, **w2v))))
+                                         dict(concurrent=min(len(streams), n_replicates - g0), **w2v))))
         for k, job in jobs:
             with torch.cuda.stream(streams[k]):
                 sims = job.finish(keep_model=keep_model).cpu().numpy()
@@ -263,22 +275,22 @@ def run_genewalk(mg, genes, nreps_graph=3, nreps_null=3, alpha_fdr=1, gene_id_ty
     local_sims, local_null, nvs = {}, {}, {}
     units = plan_units(nreps_graph, nreps_null, ws, rank)
     cur = torch.cuda.current_stream()
-    nstreams = max(1, min(int(concurrent), len(units)))
+    nstreams = max(1, min(fit_concurrent(concurrent, csr.nnz), len(units)))
     streams = [torch.cuda.Stream() for _ in range(nstreams)]
-    shared = nstreams > 1
     for g0 in range(0, len(units), nstreams):
         jobs = []
+        together = min(nstreams, len(units) - g0)   # they share the GPU's resident workers
         for k, (kind, rep) in enumerate(units[g0:g0 + nstreams]):
             streams[k].wait_stream(cur)
             with torch.cuda.stream(streams[k]):
                 if kind == KIND_REAL:
                     logger.info('real replicate %d/%d on rank %d' % (rep + 1, nreps_graph, rank))
                     jobs.append((k, kind, rep, real_replicate(csr, base_seed, rep, dim_rep, wait=False,
-                                                              shared_sm=shared, **w2v)))
+                                                              concurrent=together, **w2v)))
                 else:
                     logger.info('null replicate %d/%d on rank %d' % (rep + 1, nreps_null, rank))
                     jobs.append((k, kind, rep, _NullJob(mg, base_seed, rep, dim_rep, 10, 100,
-                                                        dict(shared_sm=shared, **w2v))))
+                                                        dict(concurrent=together, **w2v))))
         for k, kind, rep, job in jobs:
             with torch.cuda.stream(streams[k]):
                 if kind == KIND_REAL:

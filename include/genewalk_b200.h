@@ -134,20 +134,32 @@ int gw_sgns_init(int32_t n, int32_t d, const int32_t *rank_of_node, const float 
  * arithmetic unfused fp32; the dot product sums d/2 (<= 32) chunks left to right and combines the
  * chunk sums by a pairwise tree.  d in {8,16,32,64,128}; K <= 32; L <= 4096.
  * A negative token ends its walk early (ragged corpora are padded with -1).
- * shared_sm != 0: the kernel keeps the noise table in global memory (L1/L2) instead of copying it
- * into ~150 KB of shared memory per CTA, so that kernels of other replicates, launched on other
- * streams, can run on the same SMs (independent replicates have independent tables: training
- * several at once relieves the same-row reduction contention in L2). */
+ * flags (gw_sgns_flags):
+ *   GW_SGNS_SHARED_SM  the kernel keeps the noise table in global memory (L1/L2) instead of copying
+ *     it into ~150 KB of shared memory per CTA, so that kernels of other replicates, launched on
+ *     other streams, can run on the same SMs (independent replicates have independent tables:
+ *     training several at once relieves the same-row reduction contention in L2).
+ *   GW_SGNS_PER_PAIR / GW_SGNS_MERGED  how a worker's updates of the rows it visits twice reach
+ *     memory.  PER_PAIR: one reduction per (pair, row) in gensim's order (default when lanes == 1;
+ *     this is gensim's order).  MERGED: the two updates of syn1neg[centre] inside a step, and the
+ *     two updates of syn0[walk[j]] from steps j-1 and j+1, are summed in registers and reduced once
+ *     (default when lanes > 1, where the interleaving with other workers' updates is arbitrary
+ *     anyway); rows are still read from the table right before use and the worker adds its own
+ *     held-back update, so its arithmetic sees every one of its updates.  Both orders are bit-exact
+ *     against the oracle when run with lanes == 1. */
+enum gw_sgns_flags { GW_SGNS_SHARED_SM = 1, GW_SGNS_PER_PAIR = 2, GW_SGNS_MERGED = 4 };
 int gw_sgns_train(int32_t n, int32_t d, const int32_t *tokens, int64_t W, int32_t L,
                   int32_t window, int32_t K, int32_t epochs, int32_t epoch_begin,
                   int32_t epoch_end, double alpha0, double alpha_min, int64_t job_walks,
                   int64_t chunk_walks, int64_t streams, const gw_alias_entry *alias_table,
-                  float *syn0, float *syn1neg, uint64_t seed, int64_t lanes, int32_t shared_sm,
+                  float *syn0, float *syn1neg, uint64_t seed, int64_t lanes, int32_t flags,
                   gw_stream_t stream);
 
-/* the (lanes, chunk_walks, streams) gw_sgns_train uses when they are passed as 0 (host pointers) */
-int gw_sgns_auto_shape(int32_t n, int64_t W, int64_t job_walks, int64_t *lanes_out,
-                       int64_t *chunk_out, int64_t *streams_out);
+/* the (lanes, chunk_walks, streams) gw_sgns_train uses when they are passed as 0 (host pointers).
+ * concurrent = number of trainings the caller runs at once on this GPU (separate streams, flag
+ * GW_SGNS_SHARED_SM): they share the GPU's resident workers; gw_sgns_train itself assumes 1. */
+int gw_sgns_auto_shape(int32_t n, int64_t W, int64_t job_walks, int32_t concurrent,
+                       int64_t *lanes_out, int64_t *chunk_out, int64_t *streams_out);
 
 /* ---- (4) similarity statistics ------------------------------------------------------------ */
 

@@ -190,6 +190,42 @@ static float dot_rows(const float *a, const float *b, int d)
     return c[0];
 }
 
+/* negative t (1..K) of the current pair */
+static int32_t draw_target(int sampler, draw_state *ds, int32_t V, int t)
+{
+    if (sampler == 0) {
+        uint32_t x = (uint32_t)((ds->next_random >> 16) % ds->cum_table[ds->cum_len - 1]);
+        int32_t target = bisect_left_u32(ds->cum_table, 0, ds->cum_len, x);
+        ds->next_random = (ds->next_random * 25214903917ULL + 11ULL) & 281474976710655ULL;
+        return target;
+    }
+    const int w = 2 * (t - 1); /* words w, w+1 of the pair's Philox stream */
+    if ((w >> 2) != ds->n_drawn) {
+        uint32_t ctr[4] = {ds->ctr_p_lo, ds->ctr_p_hi, ds->ctr_base | (uint32_t)(w >> 2), ds->ctr_tag};
+        gwo_philox4x32_10(ctr, ds->key, ds->rnd);
+        ds->n_drawn = w >> 2;
+    }
+    const uint32_t x0 = ds->rnd[w & 3], x1 = ds->rnd[(w & 3) + 1];
+    const int32_t slot = (int32_t)(((uint64_t)x0 * (uint32_t)V) >> 32);
+    /* 16-bit coin against the slot's acceptance threshold floor(prob * 2^16) (<= 65535) */
+    uint32_t thr = (uint32_t)floorf(ds->alias_prob[slot] * 65536.0f);
+    if (thr > 65535u) thr = 65535u;
+    return ((x1 >> 16) < thr) ? slot : ds->alias_idx[slot];
+}
+
+/* sigmoid through gensim's EXP_TABLE; returns 0 when f is saturated (the target is skipped).
+ * For the largest floats below 6, f + 6 rounds up to 12.0f and gensim's index becomes 1000, one past
+ * its table (it then reads the adjacent static array); clamped to the last entry. */
+static int table_sigmoid(float f, const float *exp_table, float *sig)
+{
+    if (f <= -(float)GWO_MAX_EXP || f >= (float)GWO_MAX_EXP) return 0;
+    int ei = (int)((double)(f + (float)GWO_MAX_EXP) *
+                   ((double)GWO_EXP_TABLE_SIZE / (double)GWO_MAX_EXP / 2.0));
+    if (ei >= GWO_EXP_TABLE_SIZE) ei = GWO_EXP_TABLE_SIZE - 1;
+    *sig = exp_table[ei];
+    return 1;
+}
+
 /* one (centre, context) pair: gensim w2v_fast_sentence_sg_neg (word2vec_inner.pyx) */
 static void pair_update(int sampler, draw_state *ds, int32_t V, int32_t d, int32_t K,
                         int32_t centre, int32_t context, float alpha, const float *exp_table,
@@ -204,42 +240,109 @@ static void pair_update(int sampler, draw_state *ds, int32_t V, int32_t d, int32
             target = centre;
             label = 1.0f;
         } else {
-            if (sampler == 0) {
-                uint32_t x = (uint32_t)((ds->next_random >> 16) % ds->cum_table[ds->cum_len - 1]);
-                target = bisect_left_u32(ds->cum_table, 0, ds->cum_len, x);
-                ds->next_random = (ds->next_random * 25214903917ULL + 11ULL) & 281474976710655ULL;
-            } else {
-                const int w = 2 * (t - 1); /* words w, w+1 of the pair's Philox stream */
-                if ((w >> 2) != ds->n_drawn) {
-                    uint32_t ctr[4] = {ds->ctr_p_lo, ds->ctr_p_hi, ds->ctr_base | (uint32_t)(w >> 2),
-                                       ds->ctr_tag};
-                    gwo_philox4x32_10(ctr, ds->key, ds->rnd);
-                    ds->n_drawn = w >> 2;
-                }
-                const uint32_t x0 = ds->rnd[w & 3], x1 = ds->rnd[(w & 3) + 1];
-                const int32_t slot = (int32_t)(((uint64_t)x0 * (uint32_t)V) >> 32);
-                /* 16-bit coin against the slot's acceptance threshold floor(prob * 2^16) (<= 65535) */
-                uint32_t thr = (uint32_t)floorf(ds->alias_prob[slot] * 65536.0f);
-                if (thr > 65535u) thr = 65535u;
-                target = ((x1 >> 16) < thr) ? slot : ds->alias_idx[slot];
-            }
+            target = draw_target(sampler, ds, V, t);
             if (target == centre) continue;
             label = 0.0f;
         }
         float *row2 = syn1neg + (int64_t)target * d;
         const float f = dot_rows(row1, row2, d);
-        if (f <= -(float)GWO_MAX_EXP || f >= (float)GWO_MAX_EXP) continue;
-        /* for the largest floats below 6, f + 6 rounds up to 12.0f and gensim's index becomes 1000,
-         * one past its table (it then reads the adjacent static array); clamped to the last entry */
-        int ei = (int)((double)(f + (float)GWO_MAX_EXP) *
-                       ((double)GWO_EXP_TABLE_SIZE / (double)GWO_MAX_EXP / 2.0));
-        if (ei >= GWO_EXP_TABLE_SIZE) ei = GWO_EXP_TABLE_SIZE - 1;
-        const float sig = exp_table[ei];
+        float sig;
+        if (!table_sigmoid(f, exp_table, &sig)) continue;
         const float g = (label - sig) * alpha;
         for (int k = 0; k < d; ++k) work[k] = work[k] + g * row2[k];
         for (int k = 0; k < d; ++k) row2[k] = row2[k] + g * row1[k];
     }
     for (int k = 0; k < d; ++k) row1[k] = row1[k] + work[k]; /* lockf == 1 */
+}
+
+/* ---- merged reduction order (the CUDA kernel's Hogwild default, GW_SGNS_MERGED) ------------------
+ * Same update rule, same pairs, same negatives; only the moment at which a worker's updates of the
+ * rows it visits twice reach the tables differs: the two updates of syn1neg[centre] inside a step
+ * (a step = both pairs of a centre) are summed and added once at the end of the step, and the two
+ * updates of syn0[walk[j]] -- from step j-1 (as right context) and step j+1 (as left context) -- are
+ * summed and added once in step j+1; in step j+1 the worker reads the row from the table and adds
+ * its own held-back update, so it computes on an up-to-date row.
+ * This restates genewalk_b200/csrc/gw_sgns_train.cu:step_update_merged operation by operation; it
+ * is NOT gensim's order (from which it differs by float summation order only). */
+static void pair_merged(int sampler, draw_state *ds, int32_t V, int32_t d, int32_t K, int32_t centre,
+                        float *ctx, float *rc, float *dC, int *anyC, float alpha,
+                        const float *exp_table, float *syn1neg, float *work)
+{
+    for (int k = 0; k < d; ++k) work[k] = 0.0f;
+    for (int t = 0; t < K + 1; ++t) {
+        float sig;
+        if (t == 0) {
+            const float f = dot_rows(ctx, rc, d);
+            if (!table_sigmoid(f, exp_table, &sig)) continue;
+            const float g = (1.0f - sig) * alpha;
+            for (int k = 0; k < d; ++k) {
+                work[k] = work[k] + g * rc[k];
+                const float delta = g * ctx[k];
+                rc[k] = rc[k] + delta;
+                dC[k] = dC[k] + delta;
+            }
+            *anyC = 1;
+        } else {
+            const int32_t target = draw_target(sampler, ds, V, t);
+            if (target == centre) continue;
+            float *row2 = syn1neg + (int64_t)target * d;
+            const float f = dot_rows(ctx, row2, d);
+            if (!table_sigmoid(f, exp_table, &sig)) continue;
+            const float g = (0.0f - sig) * alpha;
+            for (int k = 0; k < d; ++k) work[k] = work[k] + g * row2[k];
+            for (int k = 0; k < d; ++k) row2[k] = row2[k] + g * ctx[k];
+        }
+    }
+    for (int k = 0; k < d; ++k) ctx[k] = ctx[k] + work[k];
+}
+
+static void walk_merged(int sampler, draw_state *ds, int32_t V, int32_t d, int32_t K,
+                        const int32_t *walk, int len, int64_t p, int ep, float alpha,
+                        const float *exp_table, float *syn0, float *syn1neg)
+{
+    float pX[1024], pY[1024], ctxA[1024], ctxB[1024], rc[1024], dC[1024], work[1024];
+    int32_t xn = -1, yn = -1; /* nodes whose update is pending (held back), -1 = none */
+    for (int i = 0; i < len; ++i) {
+        const int32_t c = walk[i], a = i > 0 ? walk[i - 1] : -1, b = i + 1 < len ? walk[i + 1] : -1;
+        int anyC = 0;
+        for (int k = 0; k < d; ++k) {
+            rc[k] = syn1neg[(int64_t)c * d + k];
+            dC[k] = 0.0f;
+        }
+        ds->ctr_p_lo = (uint32_t)(uint64_t)p;
+        ds->ctr_p_hi = (uint32_t)((uint64_t)p >> 32);
+        ds->ctr_tag = ((uint32_t)ep << 8) | GWO_STREAM_SGNS;
+        if (a >= 0) {
+            const int pending = xn == a;
+            for (int k = 0; k < d; ++k) {
+                ctxA[k] = syn0[(int64_t)a * d + k];
+                if (pending) ctxA[k] = ctxA[k] + pX[k];
+            }
+            ds->ctr_base = (uint32_t)(2 * i) << 4;
+            ds->n_drawn = -1;
+            pair_merged(sampler, ds, V, d, K, c, ctxA, rc, dC, &anyC, alpha, exp_table, syn1neg, work);
+            if (pending)
+                for (int k = 0; k < d; ++k) work[k] = pX[k] + work[k];
+            for (int k = 0; k < d; ++k) syn0[(int64_t)a * d + k] = syn0[(int64_t)a * d + k] + work[k];
+        }
+        memcpy(pX, pY, sizeof(float) * (size_t)d);
+        xn = yn;
+        yn = -1;
+        if (b >= 0) {
+            const int back = a >= 0 && b == a;
+            for (int k = 0; k < d; ++k) ctxB[k] = back ? ctxA[k] : syn0[(int64_t)b * d + k];
+            ds->ctr_base = (uint32_t)(2 * i + 1) << 4;
+            ds->n_drawn = -1;
+            pair_merged(sampler, ds, V, d, K, c, ctxB, rc, dC, &anyC, alpha, exp_table, syn1neg, pY);
+            yn = b;
+        }
+        if (anyC)
+            for (int k = 0; k < d; ++k) syn1neg[(int64_t)c * d + k] = syn1neg[(int64_t)c * d + k] + dC[k];
+    }
+    if (xn >= 0)
+        for (int k = 0; k < d; ++k) syn0[(int64_t)xn * d + k] = syn0[(int64_t)xn * d + k] + pX[k];
+    if (yn >= 0)
+        for (int k = 0; k < d; ++k) syn0[(int64_t)yn * d + k] = syn0[(int64_t)yn * d + k] + pY[k];
 }
 
 /*
@@ -252,12 +355,13 @@ static void pair_update(int sampler, draw_state *ds, int32_t V, int32_t d, int32
  *            negative t=1..K uses words 2(t-1), 2(t-1)+1 of the concatenated stream).
  * nthreads > 1: jobs are handed to OpenMP threads and race on the tables (Hogwild, as gensim's
  *            worker threads do); nthreads == 1 is the deterministic sequential statement.
+ * merged != 0: the CUDA kernel's merged reduction order (walk_merged) instead of gensim's.
  */
 int gwo_sgns_train(int sampler, int32_t V, int32_t d, const int32_t *tokens, int64_t W, int32_t L,
                    int32_t K, int32_t epochs, double alpha0, double alpha_min, int64_t job_walks,
                    const uint32_t *cum_table, int32_t cum_len, const uint64_t *job_seeds,
                    const float *alias_prob, const int32_t *alias_idx, uint64_t seed, float *syn0,
-                   float *syn1neg, int nthreads)
+                   float *syn1neg, int nthreads, int merged)
 {
     if (V <= 0 || d <= 0 || d > 1024 || W <= 0 || L < 1 || L > 4096 || K < 0 || K > 32 ||
         epochs < 1 || epochs > 65535 || job_walks < 1)
@@ -287,6 +391,10 @@ int gwo_sgns_train(int sampler, int32_t V, int32_t d, const int32_t *tokens, int
                 for (int i = 0; i < L; ++i) walk[i] = tokens[(int64_t)i * W + p];
                 int len = 0; /* a negative token pads a ragged walk: the sentence ends there */
                 while (len < L && walk[len] >= 0) ++len;
+                if (merged) {
+                    walk_merged(sampler, &ds, V, d, K, walk, len, p, ep, alpha, exp_table, syn0, syn1neg);
+                    continue;
+                }
                 for (int i = 0; i < len; ++i) {
                     for (int j = i - 1; j <= i + 1; j += 2) { /* window = 1, reduced window 0 */
                         if (j < 0 || j >= len) continue;

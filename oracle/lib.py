@@ -47,7 +47,7 @@ def lib():
             ctypes.c_int, ctypes.c_int32, ctypes.c_int32, c_i32p, ctypes.c_int64, ctypes.c_int32,
             ctypes.c_int32, ctypes.c_int32, ctypes.c_double, ctypes.c_double, ctypes.c_int64,
             c_u32p, ctypes.c_int32, c_u64p, c_f32p, c_i32p, ctypes.c_uint64, c_f32p, c_f32p,
-            ctypes.c_int]
+            ctypes.c_int, ctypes.c_int]
         L.gwo_sgns_train.restype = ctypes.c_int
         L.gwo_max_threads.argtypes = []
         L.gwo_max_threads.restype = ctypes.c_int
@@ -93,8 +93,9 @@ def exp_table():
 
 def sgns_train(tokens, V, d, syn0, syn1neg, sampler, K=5, epochs=5, alpha0=0.025,
                alpha_min=0.0001, job_walks=1000, cum_table=None, job_seeds=None, alias_prob=None,
-               alias_idx=None, seed=0, nthreads=1):
-    """tokens: int32 [L, W] position-major; syn0/syn1neg float32 [V, d] updated in place."""
+               alias_idx=None, seed=0, nthreads=1, merged=False):
+    """tokens: int32 [L, W] position-major; syn0/syn1neg float32 [V, d] updated in place.
+    merged=True: the CUDA kernel's merged reduction order (gw_oracle.c:walk_merged)."""
     tokens = np.ascontiguousarray(tokens, dtype=np.int32)
     L, W = tokens.shape
     assert syn0.dtype == np.float32 and syn0.flags.c_contiguous and syn0.shape == (V, d)
@@ -115,7 +116,7 @@ def sgns_train(tokens, V, d, syn0, syn1neg, sampler, K=5, epochs=5, alpha0=0.025
                               int(job_walks), _p(cum_table, c_u32p), int(cum_len),
                               _p(job_seeds, c_u64p), _p(alias_prob, c_f32p),
                               _p(alias_idx, c_i32p), int(seed), _p(syn0, c_f32p),
-                              _p(syn1neg, c_f32p), int(nthreads))
+                              _p(syn1neg, c_f32p), int(nthreads), 1 if merged else 0)
     if rc != 0:
         raise RuntimeError('gwo_sgns_train rc=%d' % rc)
 

@@ -247,7 +247,7 @@ def sgns_case(n, m, niter, L, d, K, epochs, seed):
 
 
 def gpu_sgns(tok, n, d, K, epochs, prob, alias, syn0, syn1, seed, lanes, job_walks=1000,
-             alpha0=0.025, alpha_min=0.0001, chunk_walks=0, streams=0, shared_sm=0):
+             alpha0=0.025, alpha_min=0.0001, chunk_walks=0, streams=0, shared_sm=0, flags=0):
     L, W = tok.shape
     table = np.empty((n, 2), dtype=np.int32)
     table[:, 0] = prob.view(np.int32)
@@ -255,7 +255,7 @@ def gpu_sgns(tok, n, d, K, epochs, prob, alias, syn0, syn1, seed, lanes, job_wal
     d0, d1 = dev(syn0), dev(syn1)
     _lib.call('gw_sgns_train', n, d, _lib.ptr(dev(tok, np.int32)), W, L, 1, K, epochs, 0, epochs,
               alpha0, alpha_min, job_walks, chunk_walks, streams, _lib.ptr(dev(table)), _lib.ptr(d0), _lib.ptr(d1),
-              seed, lanes, shared_sm, st())
+              seed, lanes, shared_sm | flags, st())
     torch.cuda.synchronize()
     return d0.cpu().numpy(), d1.cpu().numpy()
 
@@ -279,6 +279,40 @@ def test_sgns_sequential_bit_exact(n, m, niter, L, d, K, epochs):
                               job_walks=100, shared_sm=shared_sm)
         assert np.array_equal(got0.view(np.uint32), want0.view(np.uint32))
         assert np.array_equal(got1.view(np.uint32), want1.view(np.uint32))
+
+
+@pytest.mark.parametrize('n,m,niter,L,d,K,epochs', [(40, 120, 3, 10, 8, 5, 5),
+                                                    (40, 120, 2, 10, 16, 5, 2),
+                                                    (25, 60, 1, 6, 64, 5, 1),
+                                                    (25, 60, 1, 6, 128, 5, 1),
+                                                    (30, 90, 2, 7, 32, 5, 2),
+                                                    (12, 14, 6, 10, 8, 5, 3)])
+def test_sgns_merged_reductions_bit_exact(n, m, niter, L, d, K, epochs):
+    """GW_SGNS_MERGED (the Hogwild default) run sequentially: a worker sums its two updates of a row
+    in registers and reduces once, computing on its own up-to-date view meanwhile.  Bit-exact against
+    the oracle's restatement of that order (gw_oracle.c:walk_merged), which differs from gensim's
+    per-pair order by float summation order only (amplified by the 1000-bin sigmoid table: the two
+    orders drift apart by ~1e-3 per epoch).  The 12-node case makes walks step back and revisit
+    nodes all the time; every 7th walk is cut short."""
+    tok, prob, alias, syn0, syn1 = sgns_case(n, m, niter, L, d, K, epochs, seed=11 + d)
+    tok = tok.copy()
+    tok[L // 2:, ::7] = -1
+    want0, want1 = syn0.copy(), syn1.copy()
+    olib.sgns_train(tok, n, d, want0, want1, sampler=1, K=K, epochs=epochs, job_walks=100,
+                    alias_prob=prob, alias_idx=alias, seed=77, merged=True)
+    pp0, pp1 = syn0.copy(), syn1.copy()
+    olib.sgns_train(tok, n, d, pp0, pp1, sampler=1, K=K, epochs=epochs, job_walks=100,
+                    alias_prob=prob, alias_idx=alias, seed=77)
+    assert not np.array_equal(pp0, want0) and np.abs(pp0 - want0).max() < 0.05
+    for shared_sm in (0, 1):
+        got0, got1 = gpu_sgns(tok, n, d, K, epochs, prob, alias, syn0, syn1, 77, lanes=1,
+                              job_walks=100, shared_sm=shared_sm, flags=4)
+        assert np.array_equal(got0.view(np.uint32), want0.view(np.uint32))
+        assert np.array_equal(got1.view(np.uint32), want1.view(np.uint32))
+    # and PER_PAIR can be forced in Hogwild mode (finite; not bit-comparable)
+    hw0, _ = gpu_sgns(tok, n, d, K, epochs, prob, alias, syn0, syn1, 77, lanes=8, job_walks=100,
+                      chunk_walks=4, streams=1, flags=2)
+    assert np.isfinite(hw0).all()
 
 
 def test_sgns_large_vocabulary_bit_exact():
@@ -352,10 +386,14 @@ def test_sgns_chunk_must_divide_job():
 def test_sgns_auto_shape():
     lanes, chunk, streams = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
     for n, W in ((2300, 3465000), (38000, 152681600), (1000000, 1000000000), (3, 400)):
-        _lib.call('gw_sgns_auto_shape', n, W, 1000, ctypes.byref(lanes), ctypes.byref(chunk),
-                  ctypes.byref(streams))
-        assert 1 <= lanes.value <= max(1, n // 2) and 1000 % chunk.value == 0
-        assert 1 <= streams.value <= lanes.value and lanes.value <= 160 * streams.value or n < 6400
+        alone = None
+        for conc in (1, 3, 6):
+            _lib.call('gw_sgns_auto_shape', n, W, 1000, conc, ctypes.byref(lanes), ctypes.byref(chunk),
+                      ctypes.byref(streams))
+            assert 1 <= lanes.value <= max(1, n // 2) and 1000 % chunk.value == 0
+            assert 1 <= streams.value <= lanes.value and lanes.value <= 160 * streams.value or n < 6400
+            alone = alone or lanes.value
+            assert lanes.value <= alone and lanes.value * conc <= max(alone, 148 * 128) + conc
 
 
 # ------------------------------------------------------------------------------------------------

@@ -1,26 +1,36 @@
-"""Aggregate SGNS throughput with R replicates trained concurrently on one GPU (R CUDA streams)."""
+"""Aggregate SGNS throughput with R replicates trained concurrently on one GPU (R CUDA streams).
+
+    python tools/concurrent_replicates.py R:lanes[:reductions] [R:lanes[:reductions] ...]
+"""
 import os, sys, time
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 from genewalk_b200.csr import GraphCSR
 from genewalk_b200.deepwalk import DeepWalk
 from tests import graphs
-R = int(sys.argv[1]); lanes = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 n, u, v, is_go = graphs.human_scale_edges(seed=2)
 rp, ci = graphs.csr_from_edges_numpy(n, u, v)
 csr = GraphCSR(['v%d' % i for i in range(n)], rp, ci).to_device()
+RMAX = max(int(a.split(':')[0]) for a in sys.argv[1:])
 dws = []
-for r in range(R):
+for r in range(RMAX):
     dw = DeepWalk(csr, 10, 100, seed=r + 1); dw.get_walks(); dws.append(dw)
 torch.cuda.synchronize()
-streams = [torch.cuda.Stream() for _ in range(R)]
+streams = [torch.cuda.Stream() for _ in range(RMAX)]
 W = len(dws[0].walks)
-for trial in range(2):
-    t0 = time.perf_counter()
-    outs = []
-    for r in range(R):
-        with torch.cuda.stream(streams[r]):
-            outs.append(dws[r].train_device(epochs=1, lanes=lanes, shared_sm=R > 1))
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    print('R=%d lanes=%s: %.3f s for %d epoch(s) -> %.3g pairs/s aggregate' % (R, outs[0]['lanes'], dt, R, R * W * 18 / dt), flush=True)
+for spec in sys.argv[1:]:
+    f = spec.split(':')
+    R, lanes = int(f[0]), int(f[1])
+    red = f[2] if len(f) > 2 else 'auto'
+    for trial in range(2):
+        t0 = time.perf_counter()
+        outs = []
+        for r in range(R):
+            with torch.cuda.stream(streams[r]):
+                outs.append(dws[r].train_device(epochs=2, lanes=lanes, concurrent=R, reductions=red))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    nrm = float(outs[0]['syn0'].norm(dim=1).max())
+    print('R=%d lanes=%s streams=%s red=%s: %.3f s -> %.3g pairs/s aggregate (max row norm %.2f)' %
+          (R, outs[0]['lanes'], outs[0]['streams'], red, dt, R * 2 * W * 18 / dt, nrm), flush=True)
+    del outs

@@ -145,7 +145,7 @@ def run_gpu(a):
                 dw = DeepWalk(csr, WL, NITER, seed=mix(seed, 0, rep))
                 dw.get_walks()
                 dw.word2vec(vector_size=D, negative=K, epochs=EPOCHS, sgns_seed=mix(seed, 1, rep),
-                            lanes=conc, chunk_walks=a.chunk, streams=a.streams)
+                            lanes=conc, chunk_walks=a.chunk, streams=a.streams, reductions=a.reductions)
                 sims = gw.pair_similarities(dw.model.wv, pairs).cpu().numpy()
                 torch.cuda.synchronize(); dt = time.time() - t0
                 np.save(os.path.join(a.out, '%s_gpu-%s%d_s%d_real%d.npy' % (a.case, a.tag, conc, seed, rep)), sims)
@@ -155,7 +155,7 @@ def run_gpu(a):
                 dw = DeepWalk(rg, WL, NITER, seed=mix(seed, 3, rep))
                 dw.get_walks()
                 dw.word2vec(vector_size=D, negative=K, epochs=EPOCHS, sgns_seed=mix(seed, 4, rep),
-                            lanes=conc, chunk_walks=a.chunk, streams=a.streams)
+                            lanes=conc, chunk_walks=a.chunk, streams=a.streams, reductions=a.reductions)
                 null = np.asarray(get_null_distributions(rg, dw.model.wv), dtype=np.float32)
                 torch.cuda.synchronize(); dt2 = time.time() - t1
                 np.save(os.path.join(a.out, '%s_gpu-%s%d_s%d_null%d.npy' % (a.case, a.tag, conc, seed, rep)), null)
@@ -222,6 +222,7 @@ def main():
     ap.add_argument('--chunk', type=int, default=0)
     ap.add_argument('--streams', type=int, default=0)
     ap.add_argument('--tag', default='')
+    ap.add_argument('--reductions', default='auto')
     ap.add_argument('--procs', type=int, default=os.cpu_count())
     ap.add_argument('--out', default='gpurun_out/study')
     ap.add_argument('--ref', default='oracle-gensim')
