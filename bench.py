@@ -149,7 +149,7 @@ def run_reference(args):
             'note': 'ms_per_step is the full-stage time extrapolated linearly from the sample; '
                     'gensim is not installable here, the C oracle restates it (oracle/gw_oracle.c)',
             'wall_s': time.perf_counter() - t_all}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(n, n_edges, A, scale, reps):
@@ -380,9 +380,30 @@ def run_ours(args):
         line['cpu_baseline'] = {'value': rate, 'unit': 'pairs/s', 'cores': threads, 'kind': 'port',
                                 'sample': sample}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL's version banner, torchrun) print to stdout; the contract is ONE JSON line
+    there.  Everything written to fd 1 from here on goes to stderr, emit() writes the line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    text = json.dumps(line) + '\n'
+    if _REAL_STDOUT is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, text.encode())
 
 
 def main():
@@ -401,6 +422,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours' and args.scale == 1.0:
         print('warning: fewer than 3 warm-up steps', file=sys.stderr)
+    quiet_stdout()
     if args.impl == 'reference':
         run_reference(args)
     else:
