@@ -29,6 +29,10 @@
  *                          sampler 1 "device":  Philox4x32-10 + alias table -- the sampler the CUDA
  *                                               kernel uses, so that a 1-thread CUDA run is bit-exact
  *                                               against this function.
+ *                        Two reduction orders: gensim's per-pair order (merged = 0) and the order
+ *                        of the kernel's Hogwild mode (merged = 1, see walk_merged); both are
+ *                        pinned bit for bit by the independent pure-Python statement in
+ *                        oracle/sgns_py.py (tests/test_oracle.py).
  *
  * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off, so no FMA contraction: every float op
  * rounds separately, which is what the CUDA kernel does with __fmul_rn/__fadd_rn).

@@ -293,3 +293,47 @@ def test_sgns_oracle_threads_smoke():
     tok = olib.walk_uniform(csr.row_ptr, csr.col_idx, 40, 10, 1, 0)
     itn, syn0, _ = olib.word2vec_gensim_like(tok, csr.n, nthreads=2)
     assert np.isfinite(syn0).all() and len(itn) == csr.n
+
+
+@pytest.mark.parametrize('merged', [False, True])
+@pytest.mark.parametrize('d', [8, 16])
+def test_sgns_c_oracle_matches_python_statement(merged, d):
+    """oracle/gw_oracle.c (per-pair = gensim's order, and the kernel's merged order) against the
+    pure-Python statement of the same definitions, bit for bit; ragged walks, walks that step back,
+    repeated negatives and negatives equal to the centre all occur on this 9-node graph."""
+    from oracle import sgns_py
+    from tests import graphs
+    n = 9
+    row_ptr, col_idx = graphs.csr_arrays(n, 12, seed=4, self_loops=1)
+    tok = olib.walk_uniform(row_ptr, col_idx, 2, 10, 3).copy()
+    tok[6:, ::3] = -1
+    counts = np.bincount(tok[tok >= 0].ravel(), minlength=n)
+    prob, alias = olib.alias_table(counts)
+    syn0, syn1 = olib.gensim_init_weights(n, d, seed=1)
+    want0, want1 = syn0.copy(), syn1.copy()
+    sgns_py.train(tok, n, want0, want1, prob, alias, 99, olib.exp_table(), epochs=2, job_walks=10,
+                  merged=merged)
+    got0, got1 = syn0.copy(), syn1.copy()
+    olib.sgns_train(tok, n, d, got0, got1, sampler=1, K=5, epochs=2, job_walks=10, alias_prob=prob,
+                    alias_idx=alias, seed=99, merged=merged)
+    assert not np.array_equal(got0, syn0)
+    assert np.array_equal(got0.view(np.uint32), want0.view(np.uint32))
+    assert np.array_equal(got1.view(np.uint32), want1.view(np.uint32))
+
+
+def test_sgns_merged_order_stays_close_to_per_pair():
+    """The two orders differ by float summation order only (amplified by the 1000-bin sigmoid
+    table): same structure learned, small drift."""
+    csr = _ring_of_cliques()
+    n = csr.n
+    tok = olib.walk_uniform(csr.row_ptr, csr.col_idx, 100, 10, 5, 0)
+    counts = np.bincount(tok.ravel(), minlength=n)
+    prob, alias = olib.alias_table(counts)
+    out = {}
+    for merged in (False, True):
+        vec, syn1 = olib.gensim_init_weights(n, 8)
+        olib.sgns_train(tok, n, 8, vec, syn1, sampler=1, alias_prob=prob, alias_idx=alias, seed=3,
+                        merged=merged)
+        out[merged] = stats_ref.null_similarities(csr.row_ptr, csr.col_idx, vec)
+    assert not np.array_equal(out[False], out[True])
+    assert np.abs(out[False] - out[True]).max() < 0.05
