@@ -361,9 +361,9 @@ def run_ours(args):
         from genewalk_b200.replicates import run_genewalk
         barrier()
         p0 = time.perf_counter()
-        df = run_genewalk(mg, genes, nreps_graph=args.pipeline, nreps_null=args.pipeline,
-                          alpha_fdr=0.1, gene_id_type='custom', base_seed=2024, lanes=args.lanes,
-                          concurrent=R)
+        df, parts = run_genewalk(mg, genes, nreps_graph=args.pipeline, nreps_null=args.pipeline,
+                                 alpha_fdr=0.1, gene_id_type='custom', base_seed=2024,
+                                 lanes=args.lanes, concurrent=R, return_parts=True)
         barrier()
         t_p = torch.tensor([time.perf_counter() - p0], dtype=torch.float64, device='cuda')
         if world > 1:
@@ -371,7 +371,7 @@ def run_ours(args):
         if rank == 0:
             line['pipeline'] = {'nreps_graph': args.pipeline, 'nreps_null': args.pipeline,
                                 'seconds': float(t_p.item()), 'rows_significant': int(len(df)),
-                                'alpha_fdr': 0.1}
+                                'alpha_fdr': 0.1, 'timings_rank0': parts['timings']}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import lib as olib
         csr.to_host()

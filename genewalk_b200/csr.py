@@ -35,7 +35,7 @@ class GraphCSR(object):
         nodes = list(graph.nodes())
         index = {v: i for i, v in enumerate(nodes)}
         n = len(nodes)
-        adj = graph.adj
+        adj = getattr(graph, '_adj', None) or graph.adj   # raw dict-of-dicts (insertion order)
         deg = np.fromiter((len(adj[v]) for v in nodes), dtype=np.int64, count=n)
         row_ptr = np.zeros(n + 1, dtype=np.int64)
         np.cumsum(deg, out=row_ptr[1:])
@@ -86,8 +86,13 @@ class GraphCSR(object):
 def multigraph_degrees(graph):
     """``[mg.degree(n) for n in mg.nodes()]``: parallel edges counted, a self-loop counts 2
     (/root/reference/genewalk/null_distributions.py:23)."""
-    return np.fromiter((d for _, d in graph.degree()), dtype=np.int64,
-                       count=graph.number_of_nodes())
+    adj = getattr(graph, '_adj', None) or graph.adj   # raw dict-of-dicts: no per-node view objects
+    if graph.is_multigraph():   # same numbers as graph.degree()
+        it = (sum(map(len, nbrs.values())) + (len(nbrs[v]) if v in nbrs else 0)
+              for v, nbrs in adj.items())
+    else:
+        it = (len(nbrs) + (1 if v in nbrs else 0) for v, nbrs in adj.items())
+    return np.fromiter(it, dtype=np.int64, count=graph.number_of_nodes())
 
 
 def coprime_stride(A, frac=0.6180339887498949):

@@ -49,7 +49,7 @@ class DeviceGraph(object):
         return rg
 
 
-def get_rand_graph(mg, seed=None, materialize=True):
+def get_rand_graph(mg, seed=None, materialize=True, degrees=None):
     """Return a random graph with the same degree distribution as the input.
 
     Parameters
@@ -64,6 +64,9 @@ def get_rand_graph(mg, seed=None, materialize=True):
         self-loops and parallel edges kept; the device CSR rides along in ``rg.graph['_gw_csr']``
         so ``run_walks``/``get_null_distributions`` do not re-extract it.  False: return the
         ``DeviceGraph`` only (no Python edge objects are created).
+    degrees : Optional[numpy.ndarray]
+        ``[mg.degree(n) for n in mg.nodes()]`` when the caller already has it (the replicate
+        drivers randomize the same network many times).
 
     Returns
     -------
@@ -73,7 +76,7 @@ def get_rand_graph(mg, seed=None, materialize=True):
     import torch
     _lib.require_cuda()
     # this is not randomized: order is same (null_distributions.py:22-23)
-    d_seq = np.sort(multigraph_degrees(mg))[::-1].astype(np.int32)
+    d_seq = np.sort(multigraph_degrees(mg) if degrees is None else np.asarray(degrees))[::-1].astype(np.int32)
     n = len(d_seq)
     S = int(d_seq.astype(np.int64).sum())
     if S % 2 != 0:

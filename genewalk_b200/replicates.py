@@ -15,7 +15,7 @@ import random
 import numpy as np
 
 from . import _lib
-from .csr import GraphCSR
+from .csr import GraphCSR, multigraph_degrees
 from .deepwalk import DeepWalk
 from .null_distributions import get_rand_graph
 from .perform_statistics import GeneWalk
@@ -156,10 +156,11 @@ def real_replicate(csr, base_seed, rep, dim_rep=8, walk_length=10, niter=100, wa
 class _NullJob(object):
     """A null replicate in flight: randomized graph, walks and training enqueued on a stream."""
 
-    def __init__(self, mg, base_seed, rep, dim_rep, walk_length, niter, w2v):
+    def __init__(self, mg, base_seed, rep, dim_rep, walk_length, niter, w2v, degrees=None):
         import torch
         self.dim_rep = dim_rep
-        self.rg = get_rand_graph(mg, seed=mix_seed(base_seed, 2, rep), materialize=False)
+        self.rg = get_rand_graph(mg, seed=mix_seed(base_seed, 2, rep), materialize=False,
+                                 degrees=degrees)
         self.dw = DeepWalk(self.rg, walk_length, niter, seed=mix_seed(base_seed, 3, rep))
         self.dw.get_walks()
         if len(self.dw.walks) > 0:
@@ -196,32 +197,56 @@ def null_replicate(mg, base_seed, rep, dim_rep=8, walk_length=10, niter=100, **w
     return job.finish(), job.dw
 
 
+def _run_rolling(n_units, nstreams, enqueue, finish):
+    """Keeps up to ``nstreams`` units in flight, unit i on CUDA stream i % nstreams: before unit i is
+    enqueued, unit i - nstreams (the previous one on that stream) is finished, so there is no
+    barrier between rounds -- the other streams keep the GPU busy meanwhile -- and at most
+    ``nstreams`` walk corpora are alive.  ``enqueue(i, together)`` and ``finish(i, job)`` run with
+    the unit's stream current; ``together`` = number of units of the unit's round (the last round
+    may be smaller: its trainings take a larger share of the GPU's workers).  Units are finished in
+    order."""
+    import torch
+    cur = torch.cuda.current_stream()
+    nstreams = max(1, min(int(nstreams), n_units))
+    streams = [torch.cuda.Stream() for _ in range(nstreams)] if nstreams > 1 else [cur]
+    for st in streams:
+        if st is not cur:
+            st.wait_stream(cur)
+    inflight = [None] * nstreams
+    for i in range(n_units):
+        k = i % nstreams
+        with torch.cuda.stream(streams[k]):
+            if inflight[k] is not None:
+                finish(*inflight[k])
+            inflight[k] = (i, enqueue(i, min(nstreams, n_units - (i - k))))
+    for k in sorted((k for k in range(nstreams) if inflight[k] is not None),
+                    key=lambda k: inflight[k][0]):
+        with torch.cuda.stream(streams[k]):
+            finish(*inflight[k])
+    for st in streams:
+        if st is not cur:
+            cur.wait_stream(st)
+
+
 def run_walks_many(graph, n_replicates, base_seed=None, concurrent=DEFAULT_CONCURRENT,
                    walk_length=10, niter=100, vector_size=8, **w2v):
     """``[run_walks(graph, ...) for _ in range(n_replicates)]`` (cli.py:200-203) with up to
     ``concurrent`` replicates trained at once on separate CUDA streams.  Returns the DeepWalk
     objects (``.model.wv`` set)."""
-    import torch
     _lib.require_cuda()
     if base_seed is None:
         base_seed = random.getrandbits(64)
     csr = GraphCSR.from_networkx(graph).to_device() if not isinstance(graph, GraphCSR) else graph.to_device()
     out = []
-    cur = torch.cuda.current_stream()
-    concurrent = fit_concurrent(concurrent, csr.nnz, niter, walk_length)
-    streams = [torch.cuda.Stream() for _ in range(max(1, min(concurrent, n_replicates)))]
-    for g0 in range(0, n_replicates, len(streams)):
-        group = []
-        for k, rep in enumerate(range(g0, min(n_replicates, g0 + len(streams)))):
-            streams[k].wait_stream(cur)
-            with torch.cuda.stream(streams[k]):
-                group.append((k, real_replicate(csr, base_seed, rep, vector_size, walk_length, niter,
-                                                wait=False, concurrent=min(len(streams), n_replicates - g0), **w2v)))
-        for k, dw in group:
-            with torch.cuda.stream(streams[k]):
-                dw.finish_word2vec()
-            cur.wait_stream(streams[k])
-            out.append(dw)
+
+    def enqueue(rep, together):
+        return real_replicate(csr, base_seed, rep, vector_size, walk_length, niter, wait=False,
+                              concurrent=together, **w2v)
+
+    def finish(rep, dw):
+        dw.finish_word2vec()
+        out.append(dw)
+    _run_rolling(n_replicates, fit_concurrent(concurrent, csr.nnz, niter, walk_length), enqueue, finish)
     return out
 
 
@@ -229,26 +254,20 @@ def null_replicates_many(mg, n_replicates, base_seed=None, concurrent=DEFAULT_CO
                          walk_length=10, niter=100, vector_size=8, keep_model=True, **w2v):
     """The body of the null_distribution loop (cli.py:219-236) for ``n_replicates`` randomized
     networks, up to ``concurrent`` at once: ``[(DeepWalk, null similarities as numpy float32)]``."""
-    import torch
     _lib.require_cuda()
     if base_seed is None:
         base_seed = random.getrandbits(64)
     out = []
-    cur = torch.cuda.current_stream()
-    concurrent = fit_concurrent(concurrent, sum(d for _, d in mg.degree()), niter, walk_length)
-    streams = [torch.cuda.Stream() for _ in range(max(1, min(concurrent, n_replicates)))]
-    for g0 in range(0, n_replicates, len(streams)):
-        jobs = []
-        for k, rep in enumerate(range(g0, min(n_replicates, g0 + len(streams)))):
-            streams[k].wait_stream(cur)
-            with torch.cuda.stream(streams[k]):
-                jobs.append((k, _NullJob(mg, base_seed, rep, vector_size, walk_length, niter,
-                                         dict(concurrent=min(len(streams), n_replicates - g0), **w2v))))
-        for k, job in jobs:
-            with torch.cuda.stream(streams[k]):
-                sims = job.finish(keep_model=keep_model).cpu().numpy()
-            cur.wait_stream(streams[k])
-            out.append((job.dw, sims))
+
+    def enqueue(rep, together):
+        return _NullJob(mg, base_seed, rep, vector_size, walk_length, niter,
+                        dict(concurrent=together, **w2v), degrees=degrees)
+
+    def finish(rep, job):
+        out.append((job.dw, job.finish(keep_model=keep_model).cpu().numpy()))
+    degrees = multigraph_degrees(mg)
+    _run_rolling(n_replicates, fit_concurrent(concurrent, int(degrees.sum()), niter, walk_length),
+                 enqueue, finish)
     return out
 
 
@@ -259,9 +278,11 @@ def run_genewalk(mg, genes, nreps_graph=3, nreps_null=3, alpha_fdr=1, gene_id_ty
     assembled ``nx.MultiGraph``; replicates are sharded over the ranks of the initialised process
     group (one process per GPU) and, on every GPU, up to ``concurrent`` of them are trained at once
     on separate CUDA streams.  Returns the results DataFrame (identical on every rank)."""
+    import time
     import torch
     _lib.require_cuda()
     ws, rank = world()
+    t_start = time.perf_counter()
     if base_seed is None:
         base_seed = random.getrandbits(64)
         if ws > 1:   # all ranks must agree on the seed: rank 0's draw wins
@@ -274,34 +295,31 @@ def run_genewalk(mg, genes, nreps_graph=3, nreps_null=3, alpha_fdr=1, gene_id_ty
     m = len(pairs['pair_go'])
     local_sims, local_null, nvs = {}, {}, {}
     units = plan_units(nreps_graph, nreps_null, ws, rank)
-    cur = torch.cuda.current_stream()
-    nstreams = max(1, min(fit_concurrent(concurrent, csr.nnz), len(units)))
-    streams = [torch.cuda.Stream() for _ in range(nstreams)]
-    for g0 in range(0, len(units), nstreams):
-        jobs = []
-        together = min(nstreams, len(units) - g0)   # they share the GPU's resident workers
-        for k, (kind, rep) in enumerate(units[g0:g0 + nstreams]):
-            streams[k].wait_stream(cur)
-            with torch.cuda.stream(streams[k]):
-                if kind == KIND_REAL:
-                    logger.info('real replicate %d/%d on rank %d' % (rep + 1, nreps_graph, rank))
-                    jobs.append((k, kind, rep, real_replicate(csr, base_seed, rep, dim_rep, wait=False,
-                                                              concurrent=together, **w2v)))
-                else:
-                    logger.info('null replicate %d/%d on rank %d' % (rep + 1, nreps_null, rank))
-                    jobs.append((k, kind, rep, _NullJob(mg, base_seed, rep, dim_rep, 10, 100,
-                                                        dict(concurrent=together, **w2v))))
-        for k, kind, rep, job in jobs:
-            with torch.cuda.stream(streams[k]):
-                if kind == KIND_REAL:
-                    job.finish_word2vec()
-                    nvs[rep] = job.model.wv
-                    local_sims[rep] = gw.pair_similarities(job.model.wv, pairs)
-                    job.walks = []            # release the token array
-                else:
-                    local_null[rep] = job.finish()
-                    job.dw.walks = []
-            cur.wait_stream(streams[k])
+    degrees = multigraph_degrees(mg) if any(k == KIND_NULL for k, _ in units) else None
+    t_setup = time.perf_counter()
+
+    def enqueue(i, together):
+        kind, rep = units[i]
+        if kind == KIND_REAL:
+            logger.info('real replicate %d/%d on rank %d' % (rep + 1, nreps_graph, rank))
+            return real_replicate(csr, base_seed, rep, dim_rep, wait=False, concurrent=together, **w2v)
+        logger.info('null replicate %d/%d on rank %d' % (rep + 1, nreps_null, rank))
+        return _NullJob(mg, base_seed, rep, dim_rep, 10, 100, dict(concurrent=together, **w2v),
+                        degrees=degrees)
+
+    def finish(i, job):
+        kind, rep = units[i]
+        if kind == KIND_REAL:
+            job.finish_word2vec()
+            nvs[rep] = job.model.wv
+            local_sims[rep] = gw.pair_similarities(job.model.wv, pairs)
+            job.walks = []            # release the token array
+        else:
+            local_null[rep] = job.finish()
+            job.dw.walks = []
+    _run_rolling(len(units), fit_concurrent(concurrent, csr.nnz), enqueue, finish)
+    torch.cuda.synchronize()
+    t_units = time.perf_counter()
     dev = torch.device('cuda')
     sims, nulls = exchange_results(local_sims, local_null, nreps_graph, nreps_null, m, dev, group)
     pooled = torch.cat(nulls) if nulls else torch.zeros(0, dtype=torch.float32, device=dev)
@@ -311,7 +329,13 @@ def run_genewalk(mg, genes, nreps_graph=3, nreps_null=3, alpha_fdr=1, gene_id_ty
     gw.srd = pooled.cpu().numpy()
     gw._d_srd = pooled
     gw.nvs = [nvs.get(r) for r in range(nreps_graph)]
+    t_exchange = time.perf_counter()
     df = gw.generate_output(alpha_fdr=alpha_fdr, sims=sims, pairs=pairs)
+    t_end = time.perf_counter()
+    timings = {'setup_s': t_setup - t_start, 'replicates_s': t_units - t_setup,
+               'exchange_s': t_exchange - t_units, 'statistics_s': t_end - t_exchange}
+    logger.info('run_genewalk timings: %s' % timings)
     if return_parts:
-        return df, {'sims': sims, 'null': gw.srd, 'nvs': nvs, 'base_seed': base_seed}
+        return df, {'sims': sims, 'null': gw.srd, 'nvs': nvs, 'base_seed': base_seed,
+                    'timings': timings}
     return df

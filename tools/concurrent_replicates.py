@@ -1,6 +1,9 @@
 """Aggregate SGNS throughput with R replicates trained concurrently on one GPU (R CUDA streams).
 
-    python tools/concurrent_replicates.py R:lanes[:reductions] [R:lanes[:reductions] ...]
+    python tools/concurrent_replicates.py [--sorted|--shuffled] R:lanes[:reductions] [R:lanes[:reductions] ...]
+
+--sorted relabels the nodes by descending degree (the labelling of a get_rand_graph network),
+--shuffled by a random permutation; default is the generator's labelling.
 """
 import os, sys, time
 import numpy as np, torch
@@ -9,6 +12,14 @@ from genewalk_b200.csr import GraphCSR
 from genewalk_b200.deepwalk import DeepWalk
 from tests import graphs
 n, u, v, is_go = graphs.human_scale_edges(seed=2)
+mode = [a for a in sys.argv[1:] if a.startswith('--')]
+sys.argv = [a for a in sys.argv if not a.startswith('--')]
+if mode:
+    deg = np.bincount(np.concatenate([u, v]), minlength=n)
+    order = np.argsort(-deg, kind='stable') if mode[0] == '--sorted' else np.random.default_rng(0).permutation(n)
+    new_id = np.empty(n, np.int64); new_id[order] = np.arange(n)
+    u, v = new_id[u], new_id[v]
+    print('labelling:', mode[0], flush=True)
 rp, ci = graphs.csr_from_edges_numpy(n, u, v)
 csr = GraphCSR(['v%d' % i for i in range(n)], rp, ci).to_device()
 RMAX = max(int(a.split(':')[0]) for a in sys.argv[1:])
