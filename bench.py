@@ -371,7 +371,9 @@ def run_ours(args):
         if rank == 0:
             line['pipeline'] = {'nreps_graph': args.pipeline, 'nreps_null': args.pipeline,
                                 'seconds': float(t_p.item()), 'rows_significant': int(len(df)),
-                                'alpha_fdr': 0.1, 'timings_rank0': parts['timings']}
+                                'alpha_fdr': 0.1, 'timings_rank0': parts['timings'],
+                                'timeline_rank0_ms': [[u[0], u[1], k, round(b), round(e)]
+                                                      for u, k, b, e in parts['timeline']]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import lib as olib
         csr.to_host()

@@ -42,12 +42,32 @@ void count_launch();
         if (_rc != GW_OK) return _rc; \
     } while (0)
 
+// The default memory pool hands unused memory back to the OS at every synchronisation point
+// (release threshold 0), and that release waits for the whole device like cudaFree does: with
+// several replicates in flight on different streams, one stream's host synchronisation would then
+// stall until all other streams have drained (measured: 6-10 s bubbles in the replicate pipeline).
+// Keep the pool's memory instead; it is reused by the next call's temporaries.
+inline void retain_pool_memory()
+{
+    static unsigned long long done_mask = 0;   // bit per device; a benign race repeats the call
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+    if ((done_mask >> dev) & 1ULL) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long threshold = ~0ULL;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    }
+    done_mask |= 1ULL << dev;
+}
+
 // stream-ordered temporary (cudaMallocAsync); freed on the same stream by the destructor
 struct Temp {
     void *ptr = nullptr;
     cudaStream_t stream = nullptr;
     cudaError_t alloc(size_t bytes, cudaStream_t s)
     {
+        retain_pool_memory();
         stream = s;
         return cudaMallocAsync(&ptr, bytes ? bytes : 1, s);
     }

@@ -197,14 +197,15 @@ def null_replicate(mg, base_seed, rep, dim_rep=8, walk_length=10, niter=100, **w
     return job.finish(), job.dw
 
 
-def _run_rolling(n_units, nstreams, enqueue, finish):
+def _run_rolling(n_units, nstreams, enqueue, finish, timeline=None):
     """Keeps up to ``nstreams`` units in flight, unit i on CUDA stream i % nstreams: before unit i is
     enqueued, unit i - nstreams (the previous one on that stream) is finished, so there is no
     barrier between rounds -- the other streams keep the GPU busy meanwhile -- and at most
     ``nstreams`` walk corpora are alive.  ``enqueue(i, together)`` and ``finish(i, job)`` run with
     the unit's stream current; ``together`` = number of units of the unit's round (the last round
     may be smaller: its trainings take a larger share of the GPU's workers).  Units are finished in
-    order."""
+    order.  ``timeline`` (a list) receives ``(unit, stream, begin_ms, end_ms)`` of the device work
+    enqueued by ``enqueue``, measured with CUDA events relative to the first unit's begin."""
     import torch
     cur = torch.cuda.current_stream()
     nstreams = max(1, min(int(nstreams), n_units))
@@ -213,12 +214,20 @@ def _run_rolling(n_units, nstreams, enqueue, finish):
         if st is not cur:
             st.wait_stream(cur)
     inflight = [None] * nstreams
+    events = []
     for i in range(n_units):
         k = i % nstreams
         with torch.cuda.stream(streams[k]):
             if inflight[k] is not None:
                 finish(*inflight[k])
+            if timeline is not None:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e0.record()
             inflight[k] = (i, enqueue(i, min(nstreams, n_units - (i - k))))
+            if timeline is not None:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record()
+                events.append((i, k, e0, e1))
     for k in sorted((k for k in range(nstreams) if inflight[k] is not None),
                     key=lambda k: inflight[k][0]):
         with torch.cuda.stream(streams[k]):
@@ -226,6 +235,11 @@ def _run_rolling(n_units, nstreams, enqueue, finish):
     for st in streams:
         if st is not cur:
             cur.wait_stream(st)
+    if timeline is not None and events:
+        torch.cuda.synchronize()
+        origin = events[0][2]
+        timeline.extend((i, k, origin.elapsed_time(e0), origin.elapsed_time(e1))
+                        for i, k, e0, e1 in events)
 
 
 def run_walks_many(graph, n_replicates, base_seed=None, concurrent=DEFAULT_CONCURRENT,
@@ -298,11 +312,23 @@ def run_genewalk(mg, genes, nreps_graph=3, nreps_null=3, alpha_fdr=1, gene_id_ty
     degrees = multigraph_degrees(mg) if any(k == KIND_NULL for k, _ in units) else None
     t_setup = time.perf_counter()
 
+    d_pg = torch.from_numpy(np.ascontiguousarray(pairs['pair_gene'], dtype=np.int32)).cuda()
+    d_po = torch.from_numpy(np.ascontiguousarray(pairs['pair_go'], dtype=np.int32)).cuda()
+
     def enqueue(i, together):
         kind, rep = units[i]
         if kind == KIND_REAL:
             logger.info('real replicate %d/%d on rank %d' % (rep + 1, nreps_graph, rank))
-            return real_replicate(csr, base_seed, rep, dim_rep, wait=False, concurrent=together, **w2v)
+            dw = real_replicate(csr, base_seed, rep, dim_rep, wait=False, concurrent=together, **w2v)
+            # gene-GO similarities straight from the device table (rows are graph node ids, the
+            # index space of `pairs`; every node of a pair has an edge, hence walks, hence a row):
+            # perform_statistics.py:102 without the round trip through host vectors
+            sims = torch.empty(m, dtype=torch.float32, device='cuda')
+            if m > 0:
+                _lib.call('gw_cosine_pairs', int(dim_rep), _lib.ptr(dw._pending['syn0']), m,
+                          _lib.ptr(d_pg), _lib.ptr(d_po), _lib.ptr(sims), _lib.stream_ptr())
+            local_sims[rep] = sims
+            return dw
         logger.info('null replicate %d/%d on rank %d' % (rep + 1, nreps_null, rank))
         return _NullJob(mg, base_seed, rep, dim_rep, 10, 100, dict(concurrent=together, **w2v),
                         degrees=degrees)
@@ -310,14 +336,16 @@ def run_genewalk(mg, genes, nreps_graph=3, nreps_null=3, alpha_fdr=1, gene_id_ty
     def finish(i, job):
         kind, rep = units[i]
         if kind == KIND_REAL:
-            job.finish_word2vec()
-            nvs[rep] = job.model.wv
-            local_sims[rep] = gw.pair_similarities(job.model.wv, pairs)
+            if return_parts:          # host copies of the vectors only when they are asked for
+                job.finish_word2vec()
+                nvs[rep] = job.model.wv
+            job._pending = None
             job.walks = []            # release the token array
         else:
             local_null[rep] = job.finish()
             job.dw.walks = []
-    _run_rolling(len(units), fit_concurrent(concurrent, csr.nnz), enqueue, finish)
+    timeline = [] if return_parts else None
+    _run_rolling(len(units), fit_concurrent(concurrent, csr.nnz), enqueue, finish, timeline)
     torch.cuda.synchronize()
     t_units = time.perf_counter()
     dev = torch.device('cuda')
@@ -337,5 +365,6 @@ def run_genewalk(mg, genes, nreps_graph=3, nreps_null=3, alpha_fdr=1, gene_id_ty
     logger.info('run_genewalk timings: %s' % timings)
     if return_parts:
         return df, {'sims': sims, 'null': gw.srd, 'nvs': nvs, 'base_seed': base_seed,
-                    'timings': timings}
+                    'timings': timings,
+                    'timeline': [(units[i], k, b, e) for i, k, b, e in timeline]}
     return df

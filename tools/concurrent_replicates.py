@@ -3,7 +3,8 @@
     python tools/concurrent_replicates.py [--sorted|--shuffled] R:lanes[:reductions] [R:lanes[:reductions] ...]
 
 --sorted relabels the nodes by descending degree (the labelling of a get_rand_graph network),
---shuffled by a random permutation; default is the generator's labelling.
+--shuffled by a random permutation; default is the generator's labelling.  --null trains on
+configuration-model randomizations of the network (one per replicate) instead.
 """
 import os, sys, time
 import numpy as np, torch
@@ -14,7 +15,7 @@ from tests import graphs
 n, u, v, is_go = graphs.human_scale_edges(seed=2)
 mode = [a for a in sys.argv[1:] if a.startswith('--')]
 sys.argv = [a for a in sys.argv if not a.startswith('--')]
-if mode:
+if mode and mode[0] != '--null':
     deg = np.bincount(np.concatenate([u, v]), minlength=n)
     order = np.argsort(-deg, kind='stable') if mode[0] == '--sorted' else np.random.default_rng(0).permutation(n)
     new_id = np.empty(n, np.int64); new_id[order] = np.arange(n)
@@ -24,8 +25,14 @@ rp, ci = graphs.csr_from_edges_numpy(n, u, v)
 csr = GraphCSR(['v%d' % i for i in range(n)], rp, ci).to_device()
 RMAX = max(int(a.split(':')[0]) for a in sys.argv[1:])
 dws = []
+degrees = np.bincount(np.concatenate([u, v]), minlength=n)
 for r in range(RMAX):
-    dw = DeepWalk(csr, 10, 100, seed=r + 1); dw.get_walks(); dws.append(dw)
+    g = csr
+    if mode and mode[0] == '--null':
+        import networkx as nx
+        from genewalk_b200.null_distributions import get_rand_graph
+        g = get_rand_graph(nx.MultiGraph(), seed=100 + r, materialize=False, degrees=degrees)
+    dw = DeepWalk(g, 10, 100, seed=r + 1); dw.get_walks(); dws.append(dw)
 torch.cuda.synchronize()
 streams = [torch.cuda.Stream() for _ in range(RMAX)]
 W = len(dws[0].walks)
