@@ -138,9 +138,15 @@ def fit_concurrent(requested, nnz, niter=100, walk_length=10):
     """Replicates to run at once: ``requested``, capped so that their walk corpora (the only large
     per-replicate allocation: niter * nnz walks of walk_length int32 tokens) fit the free HBM."""
     import torch
+    # blocks cached by torch's allocator belong to the streams of earlier phases and cannot serve
+    # the new streams; hand them back now, while the device is idle (later, an allocation that does
+    # not fit would make the allocator free them in the middle of the run, which waits for all
+    # streams to drain)
+    torch.cuda.empty_cache()
     free, _ = torch.cuda.mem_get_info()
-    free += torch.cuda.memory_reserved() - torch.cuda.memory_allocated()   # cached by the allocator
-    per_replicate = int(1.25 * 4 * walk_length * niter * max(int(nnz), 1)) + (256 << 20)
+    # a randomized network has up to ~1.3x the adjacency entries of the real one (parallel edges of
+    # the MultiGraph become distinct neighbours), and a stream keeps its previous corpus cached
+    per_replicate = int(1.6 * 4 * walk_length * niter * max(int(nnz), 1)) + (256 << 20)
     return max(1, min(int(requested), int(0.85 * free) // per_replicate))
 
 
@@ -195,6 +201,36 @@ def null_replicate(mg, base_seed, rep, dim_rep=8, walk_length=10, niter=100, **w
     Returns (device float32 tensor of null similarities, DeepWalk)."""
     job = _NullJob(mg, base_seed, rep, dim_rep, walk_length, niter, w2v)
     return job.finish(), job.dw
+
+
+_PRELOADED = set()
+
+
+def preload_kernels(dim_rep=8, concurrent=1, **w2v):
+    """Launch every kernel of a real and a null replicate once, on a 12-node network, while the
+    device is idle.  CUDA loads a kernel at its first launch and that load waits until ALL streams
+    have drained: with replicates in flight on several streams, the first randomized network and
+    the first null-similarity call otherwise stall the host for seconds (measured: 6.6 s and 11.8 s
+    bubbles in a 20-replicate run)."""
+    import networkx as nx
+    import torch
+    key = (torch.cuda.current_device(), int(dim_rep), concurrent > 1, tuple(sorted(w2v.items())))
+    if key in _PRELOADED:
+        return
+    g = nx.MultiGraph()
+    g.add_edges_from([(i, (i + 1) % 12) for i in range(12)] + [(0, 6), (0, 6), (3, 3)])
+    csr = GraphCSR.from_networkx(g).to_device()
+    dw = real_replicate(csr, 0, 0, dim_rep, niter=2, wait=False, concurrent=concurrent, **w2v)
+    pg = torch.zeros(1, dtype=torch.int32, device='cuda')
+    one = torch.empty(1, dtype=torch.float32, device='cuda')
+    _lib.call('gw_cosine_pairs', int(dim_rep), _lib.ptr(dw._pending['syn0']), 1, _lib.ptr(pg),
+              _lib.ptr(pg), _lib.ptr(one), _lib.stream_ptr())
+    dw.finish_word2vec()
+    null = _NullJob(g, 0, 0, dim_rep, 10, 2, dict(concurrent=concurrent, **w2v)).finish()
+    if null.numel() > 0:
+        _lib.call('gw_sort_f32', _lib.ptr(null), null.numel(), _lib.stream_ptr())
+    torch.cuda.synchronize()
+    _PRELOADED.add(key)
 
 
 def _run_rolling(n_units, nstreams, enqueue, finish, timeline=None):
@@ -260,7 +296,10 @@ def run_walks_many(graph, n_replicates, base_seed=None, concurrent=DEFAULT_CONCU
     def finish(rep, dw):
         dw.finish_word2vec()
         out.append(dw)
-    _run_rolling(n_replicates, fit_concurrent(concurrent, csr.nnz, niter, walk_length), enqueue, finish)
+    nstreams = fit_concurrent(concurrent, csr.nnz, niter, walk_length)
+    if min(nstreams, n_replicates) > 1:
+        preload_kernels(vector_size, 2, **w2v)
+    _run_rolling(n_replicates, nstreams, enqueue, finish)
     return out
 
 
@@ -280,8 +319,10 @@ def null_replicates_many(mg, n_replicates, base_seed=None, concurrent=DEFAULT_CO
     def finish(rep, job):
         out.append((job.dw, job.finish(keep_model=keep_model).cpu().numpy()))
     degrees = multigraph_degrees(mg)
-    _run_rolling(n_replicates, fit_concurrent(concurrent, int(degrees.sum()), niter, walk_length),
-                 enqueue, finish)
+    nstreams = fit_concurrent(concurrent, int(degrees.sum()), niter, walk_length)
+    if min(nstreams, n_replicates) > 1:
+        preload_kernels(vector_size, 2, **w2v)
+    _run_rolling(n_replicates, nstreams, enqueue, finish)
     return out
 
 
@@ -345,7 +386,10 @@ def run_genewalk(mg, genes, nreps_graph=3, nreps_null=3, alpha_fdr=1, gene_id_ty
             local_null[rep] = job.finish()
             job.dw.walks = []
     timeline = [] if return_parts else None
-    _run_rolling(len(units), fit_concurrent(concurrent, csr.nnz), enqueue, finish, timeline)
+    nstreams = fit_concurrent(concurrent, csr.nnz)
+    if min(nstreams, len(units)) > 1:
+        preload_kernels(dim_rep, 2, **w2v)
+    _run_rolling(len(units), nstreams, enqueue, finish, timeline)
     torch.cuda.synchronize()
     t_units = time.perf_counter()
     dev = torch.device('cuda')
