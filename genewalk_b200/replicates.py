@@ -138,15 +138,16 @@ def fit_concurrent(requested, nnz, niter=100, walk_length=10):
     """Replicates to run at once: ``requested``, capped so that their walk corpora (the only large
     per-replicate allocation: niter * nnz walks of walk_length int32 tokens) fit the free HBM."""
     import torch
-    # blocks cached by torch's allocator belong to the streams of earlier phases and cannot serve
-    # the new streams; hand them back now, while the device is idle (later, an allocation that does
-    # not fit would make the allocator free them in the middle of the run, which waits for all
-    # streams to drain)
-    torch.cuda.empty_cache()
-    free, _ = torch.cuda.mem_get_info()
+    # blocks cached by torch's allocator for other streams cannot serve ours; when memory is short
+    # hand them back now, while the device is idle (later, an allocation that does not fit would
+    # make the allocator free them in the middle of the run, which waits for all streams to drain)
     # a randomized network has up to ~1.3x the adjacency entries of the real one (parallel edges of
     # the MultiGraph become distinct neighbours), and a stream keeps its previous corpus cached
     per_replicate = int(1.6 * 4 * walk_length * niter * max(int(nnz), 1)) + (256 << 20)
+    free, _ = torch.cuda.mem_get_info()
+    if int(0.85 * free) < int(requested) * per_replicate:
+        torch.cuda.empty_cache()
+        free, _ = torch.cuda.mem_get_info()
     return max(1, min(int(requested), int(0.85 * free) // per_replicate))
 
 
@@ -204,6 +205,18 @@ def null_replicate(mg, base_seed, rep, dim_rep=8, walk_length=10, niter=100, **w
 
 
 _PRELOADED = set()
+_SIDE_STREAMS = {}
+
+
+def _side_streams(count):
+    """The same stream objects on every call: torch's allocator caches blocks per stream, so a
+    later batch reuses the corpora buffers of an earlier one instead of allocating anew."""
+    import torch
+    pool = _SIDE_STREAMS.setdefault(torch.cuda.current_device(), [])
+    while len(pool) < count:
+        pool.append(torch.cuda.Stream())
+    return pool[:count]
+
 
 
 def preload_kernels(dim_rep=8, concurrent=1, **w2v):
@@ -245,7 +258,7 @@ def _run_rolling(n_units, nstreams, enqueue, finish, timeline=None):
     import torch
     cur = torch.cuda.current_stream()
     nstreams = max(1, min(int(nstreams), n_units))
-    streams = [torch.cuda.Stream() for _ in range(nstreams)] if nstreams > 1 else [cur]
+    streams = _side_streams(nstreams) if nstreams > 1 else [cur]
     for st in streams:
         if st is not cur:
             st.wait_stream(cur)
