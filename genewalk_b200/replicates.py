@@ -1,6 +1,6 @@
 """Replicate driver: the loops of /root/reference/genewalk/cli.py:200-214 (nreps_graph real-network
 replicates) and :219-238 (nreps_null randomized-network replicates, pooled and sorted null
-similarities), sharded one replicate per GPU.
+similarities), sharded over the GPUs and, on every GPU, run several at a time on CUDA streams.
 
 Replicates are independent units: unit u runs on rank u % world_size with no
 data-path collective; the only exchange is one all-gather of (a) the fixed-length gene-GO similarity
@@ -138,14 +138,15 @@ def fit_concurrent(requested, nnz, niter=100, walk_length=10):
     """Replicates to run at once: ``requested``, capped so that their walk corpora (the only large
     per-replicate allocation: niter * nnz walks of walk_length int32 tokens) fit the free HBM."""
     import torch
-    # blocks cached by torch's allocator for other streams cannot serve ours; when memory is short
-    # hand them back now, while the device is idle (later, an allocation that does not fit would
-    # make the allocator free them in the middle of the run, which waits for all streams to drain)
-    # a randomized network has up to ~1.3x the adjacency entries of the real one (parallel edges of
-    # the MultiGraph become distinct neighbours), and a stream keeps its previous corpus cached
+    # 1.6x: a randomized network has up to ~1.3x the adjacency entries of the real one (parallel
+    # edges of the MultiGraph become distinct neighbours), and a stream keeps its previous, smaller
+    # corpus buffer cached next to the new one
     per_replicate = int(1.6 * 4 * walk_length * niter * max(int(nnz), 1)) + (256 << 20)
     free, _ = torch.cuda.mem_get_info()
     if int(0.85 * free) < int(requested) * per_replicate:
+        # blocks torch's allocator caches for other streams cannot serve ours: hand them back now,
+        # while the device is idle (an allocation that does not fit later would make the allocator
+        # free them in the middle of the run, which waits for all streams to drain)
         torch.cuda.empty_cache()
         free, _ = torch.cuda.mem_get_info()
     return max(1, min(int(requested), int(0.85 * free) // per_replicate))
@@ -216,7 +217,6 @@ def _side_streams(count):
     while len(pool) < count:
         pool.append(torch.cuda.Stream())
     return pool[:count]
-
 
 
 def preload_kernels(dim_rep=8, concurrent=1, **w2v):

@@ -86,3 +86,54 @@ def test_exchange_over_gloo_world_size_2(ng, nn):
         p.join(120)
         assert p.exitcode == 0
     assert list(out) == [1] * ws
+
+
+def test_rolling_schedule_order_and_shares(monkeypatch):
+    """_run_rolling: unit i runs on stream i % nstreams, unit i - nstreams is finished right before
+    unit i is enqueued (no barrier between rounds), units finish in order, and the last, smaller
+    round is told how many units share the GPU.  CUDA streams are replaced by dummies."""
+    import contextlib
+    import torch
+    from genewalk_b200 import replicates as R
+
+    class FakeStream(object):
+        def __init__(self, name):
+            self.name, self.waited = name, []
+
+        def wait_stream(self, other):
+            self.waited.append(other.name)
+    cur = FakeStream('cur')
+    side = [FakeStream('s%d' % k) for k in range(8)]
+    active = []
+
+    @contextlib.contextmanager
+    def fake_ctx(stream):
+        active.append(stream.name)
+        yield
+        active.pop()
+    monkeypatch.setattr(torch.cuda, 'current_stream', lambda: cur)
+    monkeypatch.setattr(torch.cuda, 'stream', fake_ctx)
+    monkeypatch.setattr(R, '_side_streams', lambda count: side[:count])
+    log = []
+    R._run_rolling(8, 3, lambda i, together: log.append(('enq', i, together, active[-1])) or ('job', i),
+                   lambda i, job: log.append(('fin', i, job, active[-1])))
+    want = [('enq', 0, 3, 's0'), ('enq', 1, 3, 's1'), ('enq', 2, 3, 's2'),
+            ('fin', 0, ('job', 0), 's0'), ('enq', 3, 3, 's0'),
+            ('fin', 1, ('job', 1), 's1'), ('enq', 4, 3, 's1'),
+            ('fin', 2, ('job', 2), 's2'), ('enq', 5, 3, 's2'),
+            ('fin', 3, ('job', 3), 's0'), ('enq', 6, 2, 's0'),
+            ('fin', 4, ('job', 4), 's1'), ('enq', 7, 2, 's1'),
+            ('fin', 5, ('job', 5), 's2'), ('fin', 6, ('job', 6), 's0'), ('fin', 7, ('job', 7), 's1')]
+    assert log == want
+    assert all(s.waited == ['cur'] for s in side[:3]) and cur.waited == ['s0', 's1', 's2']
+    # a single stream degenerates to the serial loop on the current stream
+    log.clear()
+    R._run_rolling(3, 1, lambda i, together: log.append(('enq', i, together, active[-1])) or i,
+                   lambda i, job: log.append(('fin', i, job, active[-1])))
+    assert log == [('enq', 0, 1, 'cur'), ('fin', 0, 0, 'cur'), ('enq', 1, 1, 'cur'),
+                   ('fin', 1, 1, 'cur'), ('enq', 2, 1, 'cur'), ('fin', 2, 2, 'cur')]
+    # more streams than units
+    log.clear()
+    R._run_rolling(2, 6, lambda i, together: log.append(('enq', i, together)) or i,
+                   lambda i, job: log.append(('fin', i)))
+    assert log == [('enq', 0, 2), ('enq', 1, 2), ('fin', 0), ('fin', 1)]
