@@ -228,10 +228,11 @@ class DeepWalk(object):
         the queue at a time; must divide the job size; 0 = library default), ``streams`` (corpus
         slices the queue deals chunks from in turn; 0 = library default), ``concurrent`` (number of
         trainings the caller runs at once on this GPU on different CUDA streams: they share the
-        GPU's resident workers and leave the SMs' shared memory to each other; default 1), ``reductions`` ('auto' | 'per_pair' | 'merged':
-        see ``gw_sgns_flags`` in include/genewalk_b200.h), ``wait`` (False: only enqueue the training on
-        the current CUDA stream; ``finish_word2vec()`` then downloads the vectors) and ``sgns_seed``
-        (Philox key of the negative draws).
+        GPU's resident workers and leave the SMs' shared memory to each other; default 1),
+        ``reductions`` ('auto' | 'per_pair' | 'merged': see ``gw_sgns_flags`` in
+        include/genewalk_b200.h), ``wait`` (False: only enqueue the training on the current CUDA
+        stream; ``finish_word2vec()`` then downloads the vectors) and ``sgns_seed`` (Philox key of
+        the negative draws).
         """
         import torch
         _lib.require_cuda()
