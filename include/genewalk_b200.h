@@ -140,12 +140,13 @@ int gw_sgns_init(int32_t n, int32_t d, const int32_t *rank_of_node, const float 
  *     other streams, can run on the same SMs (independent replicates have independent tables:
  *     training several at once relieves the same-row reduction contention in L2).
  *   GW_SGNS_PER_PAIR / GW_SGNS_MERGED  how a worker's updates of the rows it visits twice reach
- *     memory.  PER_PAIR: one reduction per (pair, row) in gensim's order (default when lanes == 1;
- *     this is gensim's order).  MERGED: the two updates of syn1neg[centre] inside a step, and the
- *     two updates of syn0[walk[j]] from steps j-1 and j+1, are summed in registers and reduced once
- *     (default when lanes > 1, where the interleaving with other workers' updates is arbitrary
- *     anyway); rows are still read from the table right before use and the worker adds its own
- *     held-back update, so its arithmetic sees every one of its updates.  Both orders are bit-exact
+ *     memory.  PER_PAIR: one reduction per (pair, row) in gensim's order.  MERGED: the two updates
+ *     of syn1neg[centre] inside a step, and the two updates of syn0[walk[j]] from steps j-1 and
+ *     j+1, are summed in registers and reduced once; rows are still read from the table right
+ *     before use and the worker adds its own held-back update, so its arithmetic sees every one of
+ *     its updates.  Default (neither flag): MERGED when 1 < lanes <= n/12 -- many rows per worker,
+ *     where the interleaving with other workers' updates is arbitrary anyway and holding an update
+ *     back for two steps is measured to be neutral -- else PER_PAIR.  Both orders are bit-exact
  *     against the oracle when run with lanes == 1. */
 enum gw_sgns_flags { GW_SGNS_SHARED_SM = 1, GW_SGNS_PER_PAIR = 2, GW_SGNS_MERGED = 4 };
 int gw_sgns_train(int32_t n, int32_t d, const int32_t *tokens, int64_t W, int32_t L,
