@@ -351,7 +351,12 @@ def run_ours(args):
                     'frac_of_uniform': (pairs_launch / 2 / (k_eff / 1e3) / l2_peaks['uniform_rows'])
                     if l2_peaks.get('uniform_rows') else None},
                 'walk': {'steps_per_s': W * (WL - 1) / (walk_ms / 1e3), 'ms': walk_ms,
-                         'achieved_gbs': BYTES_PER_STEP * W * (WL - 1) / (walk_ms / 1e3) / 1e9},
+                         'achieved_gbs': BYTES_PER_STEP * W * (WL - 1) / (walk_ms / 1e3) / 1e9,
+                         'frac_of_l2_random_sector_rate':
+                             (W * (WL - 1) / (walk_ms / 1e3) / l2_peaks['random_sector_gathers_per_s'])
+                             if l2_peaks.get('random_sector_gathers_per_s') else None,
+                         'note': 'timed on its stream while the other replicates of the step train; '
+                                 'one random L2 sector (the neighbour) per step is the bound'},
                 'sgns_kernel_pairs_per_s': pairs_launch / (k_eff / 1e3),
                 'sgns_shape': {'lanes': dv['lanes'], 'chunk_walks': dv['chunk_walks'], 'streams': dv['streams'],
                                'job_walks': dv['job_walks']}}
