@@ -144,7 +144,7 @@ def run_gpu(a):
                 torch.cuda.synchronize(); t0 = time.time()
                 dw = DeepWalk(csr, WL, NITER, seed=mix(seed, 0, rep))
                 dw.get_walks()
-                dw.word2vec(vector_size=D, negative=K, epochs=EPOCHS, sgns_seed=mix(seed, 1, rep),
+                dw.word2vec(vector_size=D, negative=K, epochs=EPOCHS, sgns_seed=mix(seed, 1 + 16 * a.salt, rep),
                             lanes=conc, chunk_walks=a.chunk, streams=a.streams, reductions=a.reductions)
                 sims = gw.pair_similarities(dw.model.wv, pairs).cpu().numpy()
                 torch.cuda.synchronize(); dt = time.time() - t0
@@ -154,7 +154,7 @@ def run_gpu(a):
                 rg = get_rand_graph(mg, seed=mix(seed, 2, rep), materialize=False)
                 dw = DeepWalk(rg, WL, NITER, seed=mix(seed, 3, rep))
                 dw.get_walks()
-                dw.word2vec(vector_size=D, negative=K, epochs=EPOCHS, sgns_seed=mix(seed, 4, rep),
+                dw.word2vec(vector_size=D, negative=K, epochs=EPOCHS, sgns_seed=mix(seed, 4 + 16 * a.salt, rep),
                             lanes=conc, chunk_walks=a.chunk, streams=a.streams, reductions=a.reductions)
                 null = np.asarray(get_null_distributions(rg, dw.model.wv), dtype=np.float32)
                 torch.cuda.synchronize(); dt2 = time.time() - t1
@@ -223,6 +223,7 @@ def main():
     ap.add_argument('--streams', type=int, default=0)
     ap.add_argument('--tag', default='')
     ap.add_argument('--reductions', default='auto')
+    ap.add_argument('--salt', type=int, default=0, help='gpu side: perturb only the negative-sampling seeds')
     ap.add_argument('--procs', type=int, default=os.cpu_count())
     ap.add_argument('--out', default='gpurun_out/study')
     ap.add_argument('--ref', default='oracle-gensim')
