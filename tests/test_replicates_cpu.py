@@ -137,3 +137,26 @@ def test_rolling_schedule_order_and_shares(monkeypatch):
     R._run_rolling(2, 6, lambda i, together: log.append(('enq', i, together)) or i,
                    lambda i, job: log.append(('fin', i)))
     assert log == [('enq', 0, 2), ('enq', 1, 2), ('fin', 0), ('fin', 1)]
+
+
+def test_fit_concurrent_caps_by_free_memory(monkeypatch):
+    """fit_concurrent: as many replicates at once as asked for, unless their walk corpora
+    (1.6 x 4 B x walk_length x niter x adjacency entries + 256 MiB each) exceed 85 % of the free HBM;
+    the allocator cache is only released when memory is short."""
+    import torch
+    from genewalk_b200 import replicates as R
+    state = {'free': 170 << 30, 'emptied': 0}
+    monkeypatch.setattr(torch.cuda, 'mem_get_info', lambda: (state['free'], 180 << 30))
+
+    def empty():
+        state['emptied'] += 1
+        state['free'] += 8 << 30           # what the cache was holding
+    monkeypatch.setattr(torch.cuda, 'empty_cache', empty)
+    # C2: 1.53 M adjacency entries -> ~10 GB per replicate: six fit, nothing is released
+    assert R.fit_concurrent(6, 1526816) == 6 and state['emptied'] == 0
+    # C4-like: 9.8 M entries -> ~63 GB per replicate: memory is short, the cache is released, 2 fit
+    assert R.fit_concurrent(6, 9800000) == 2 and state['emptied'] == 1
+    # never below one
+    state['free'] = 1 << 30
+    assert R.fit_concurrent(6, 9800000) == 1
+    assert R.fit_concurrent(1, 10) == 1
