@@ -44,6 +44,9 @@ def build_case(name, seed):
     elif name == 'c2mod':
         mg, genes = graphs.modular_gene_go_network(20000, 18000, 400, 700000, 250000, 50000,
                                                    seed=100 + seed)
+    elif name == 'mid':  # between C1 and C2: n = 8500, ~0.2 M edges (oracle-vs-oracle floor studies)
+        mg, genes = graphs.modular_gene_go_network(4500, 4000, 100, 150000, 55000, 11000,
+                                                   seed=100 + seed)
     elif name == 'c2':   # the bench workload (BASELINE.json configs[1])
         n, u, v, is_go = graphs.human_scale_edges(seed=2 + seed)
         mg, genes = graphs.edges_to_networkx(n, u, v, is_go, 20000)
