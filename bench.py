@@ -84,7 +84,7 @@ def host_threads():
 
 
 def build_inputs(scale):
-    from tests import graphs
+    from genewalk_b200 import workloads as graphs
     ng, ngo = int(20000 * scale), int(18000 * scale)
     n, u, v, is_go = graphs.human_scale_edges(seed=2, n_genes=ng, n_go=ngo,
                                               n_gene_edges=int(700000 * scale),

@@ -19,13 +19,28 @@ def _nvcc():
     raise RuntimeError('nvcc not found')
 
 
-def needs_build():
-    if not os.path.exists(SO_PATH):
-        return True
-    so_m = os.path.getmtime(SO_PATH)
+def _deps():
     deps = [os.path.join(CSRC, f) for f in SOURCES + ['gw_common.cuh']]
     deps.append(os.path.join(HERE, '..', 'include', 'genewalk_b200.h'))
-    return any(os.path.getmtime(d) > so_m for d in deps)
+    return deps
+
+
+def source_hash():
+    """Content hash of everything the library is built from (mtimes do not survive a copy of the
+    tree to another box; contents do)."""
+    import hashlib
+    h = hashlib.sha256(' '.join(NVCC_FLAGS).encode())
+    for d in _deps():
+        with open(d, 'rb') as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def needs_build():
+    if not os.path.exists(SO_PATH) or not os.path.exists(SO_PATH + '.srchash'):
+        return True
+    with open(SO_PATH + '.srchash') as f:
+        return f.read().strip() != source_hash()
 
 
 def build(force=False, verbose=False):
@@ -42,6 +57,8 @@ def build(force=False, verbose=False):
         raise RuntimeError('nvcc failed:\n%s\n%s' % (res.stdout, res.stderr))
     if verbose:
         print(res.stderr)
+    with open(SO_PATH + '.srchash', 'w') as f:
+        f.write(source_hash())
     return SO_PATH
 
 

@@ -32,10 +32,12 @@ SIGNATURES = {
     'gw_vocab_rank': [_i32, _vp, _vp, _vp, _vp, _vp],
     'gw_alias_build': [_i32, _vp, _f64, _vp, _vp],
     'gw_sgns_init': [_i32, _i32, _vp, _vp, _vp, _vp, _vp],
-    'gw_sgns_train': [_i32, _i32, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _f64, _f64, _i64,
-                      _i64, _i64, _vp, _vp, _vp, _u64, _i64, _i32, _vp],
-    'gw_sgns_auto_shape': [_i32, _i64, _i64, _i32, ctypes.POINTER(_i64), ctypes.POINTER(_i64),
-                           ctypes.POINTER(_i64)],
+    'gw_walk_count': [_i32, _i64, _vp, _vp, _i32, _i32, _u64, _vp, _vp],
+    'gw_sgns_plan': [_i32, _vp, _i32, _i64, _i64, _i32, _vp, _i64, _vp, _vp],
+    'gw_sgns_train': [_i32, _i32, _vp, _vp, _vp, _i32, _u64, _i64, _i32, _i32, _i32, _i32, _i32, _i32,
+                      _f64, _f64, _i64, _vp, _vp, _vp, _vp, _vp, _u64, _i64, _i32, _vp],
+    'gw_sgns_auto_shape': [_i32, _i64, _i64, ctypes.POINTER(_i64), ctypes.POINTER(_i64),
+                           ctypes.POINTER(_i32)],
     'gw_cosine_pairs': [_i32, _vp, _i64, _vp, _vp, _vp, _vp],
     'gw_null_similarities': [_i32, _vp, _vp, _i32, _vp, _vp, ctypes.POINTER(_i64), _vp],
     'gw_sort_f32': [_vp, _i64, _vp],
@@ -44,6 +46,10 @@ SIGNATURES = {
     'gw_log_stats': [_vp, _i64, _i32, _vp, _vp],
     'gw_mean_sem_f32': [_vp, _i64, _i32, _vp, _vp, _vp],
 }
+
+# functions that do not return a gw_status
+INT64_RETURNS = {'gw_sgns_plan_capacity': [_i32, _i64, _i64, _i32]}
+ABI_VERSION = 200   # GW_VERSION of include/genewalk_b200.h this binding was written against
 
 _lib = None
 
@@ -61,13 +67,24 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_build.SO_PATH):
+    # rebuild when the library is missing or older than its sources (a stale .so under the same
+    # symbol names would marshal wrong arguments into the kernels)
+    if _build.needs_build():
         _build.build()
     lib = ctypes.CDLL(_build.SO_PATH)
+    lib.gw_version.restype = ctypes.c_int
+    if lib.gw_version() != ABI_VERSION:
+        raise GeneWalkCudaError('%s has ABI version %d, this package needs %d: rebuild it '
+                                '(python -m genewalk_b200._build --force)'
+                                % (_build.SO_PATH, lib.gw_version(), ABI_VERSION))
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the .so is stale: fail loudly
         fn.argtypes = argtypes
         fn.restype = ctypes.c_int
+    for name, argtypes in INT64_RETURNS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = ctypes.c_int64
     lib.gw_last_error.argtypes = []
     lib.gw_last_error.restype = ctypes.c_char_p
     lib.gw_launch_count.argtypes = []

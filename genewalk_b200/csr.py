@@ -86,6 +86,8 @@ class GraphCSR(object):
 def multigraph_degrees(graph):
     """``[mg.degree(n) for n in mg.nodes()]``: parallel edges counted, a self-loop counts 2
     (/root/reference/genewalk/null_distributions.py:23)."""
+    if hasattr(graph, 'degrees') and hasattr(graph, 'csr'):    # edgelist.EdgeListNetwork
+        return np.asarray(graph.degrees, dtype=np.int64)
     adj = getattr(graph, '_adj', None) or graph.adj   # raw dict-of-dicts: no per-node view objects
     if graph.is_multigraph():   # same numbers as graph.degree()
         it = (sum(map(len, nbrs.values())) + (len(nbrs[v]) if v in nbrs else 0)

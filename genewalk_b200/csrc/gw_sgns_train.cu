@@ -29,11 +29,14 @@ namespace gw {
 
 constexpr int kExpTableSize = 1000;
 constexpr float kMaxExp = 6.0f;
-constexpr int kTrainThreads = 512;      // upper bound of the CTA size (launch bounds)
-constexpr int kSmemAliasMaxN = 56000;   // 4 B/entry packed alias table + EXP_TABLE fit 227 KB
+constexpr int kTrainThreads = 128;      // CTA size (launch bounds)
 
 struct TrainParams {
-    const int32_t *tokens;
+    const int32_t *tokens;   // [L][W] position-major, or nullptr: the walks are regenerated
+    const int32_t *row_ptr;  // graph of the regenerated walks
+    const int32_t *col_idx;
+    int32_t niter;
+    uint32_t wkey0, wkey1;   // Philox key of the walks (gw_walk_uniform's seed)
     int64_t W;
     int32_t L;
     int32_t n;
@@ -44,18 +47,23 @@ struct TrainParams {
     double alpha_span;  // alpha0 - alpha_min
     double alpha_min;
     int64_t job_walks;    // walks per learning-rate job (gensim: 1000 walks of 10 words)
-    int64_t chunk_walks;  // walks a worker takes from the queue at a time (divides job_walks)
-    int64_t streams;      // corpus slices the queue deals chunks from in turn (see gw_sgns_train)
-    int64_t stream_chunks;  // chunks per slice
-    int32_t shared_sm;      // leave the SMs' shared memory to other kernels (concurrent replicates)
-    int32_t merge;          // merged row reductions (Hogwild mode), see step_update_merged
-    unsigned long long *job_queue;  // next job to hand out (device counter, zeroed per launch)
+    const gw_sgns_unit *units;   // the queue's work units, in the order they are handed out
+    const int64_t *num_units;
+    int64_t lanes;          // number of workers (groups beyond it, padding of the last warp, exit)
+    int32_t merge;          // merged row reductions, see step_update_merged
+    unsigned long long *job_queue;  // next unit to hand out (device counter, zeroed per launch)
     const gw_alias_entry *alias;
     const float *exp_table;  // [1000] device copy of gensim's EXP_TABLE
     float *syn0;
     float *syn1neg;
     uint32_t key0, key1;
 };
+
+// gw_sgns_auto_shape: see DESIGN.md section 4.2 and profiles/parity_study_r02.md
+constexpr int64_t kAutoLanesMax = 1024;
+constexpr int64_t kAutoRowsPerLane = 8;
+constexpr int64_t kAutoUnitWalks = 1000;
+constexpr int32_t kAutoPolicy = GW_PLAN_CHUNK;
 
 // ---- per-lane slice of a row: E consecutive floats ---------------------------------------------
 template <int E> __device__ __forceinline__ void ld_slice(const float *p, float (&r)[E])
@@ -183,7 +191,7 @@ __device__ __forceinline__ void pair_sequential(const TrainParams &P, const floa
 // A step needs 2*KT negatives = 2*ceil(KT/2) Philox calls.  Call c (pair c / CP, call c % CP of
 // that pair, CP = ceil(KT/2)) is computed by lane c % G, which also resolves the call's (up to) two
 // negatives through the alias table; resolve() then hands every lane all 2*KT targets by shuffles.
-template <int G, int KT, bool kSmemAlias> struct StepDraw {
+template <int G, int KT> struct StepDraw {
     static constexpr int CP = (KT + 1) / 2;            // Philox calls per pair
     static constexpr int NC = 2 * CP;                  // calls per step
     static constexpr int R = (NC + G - 1) / G;         // calls per lane (rounds)
@@ -191,9 +199,8 @@ template <int G, int KT, bool kSmemAlias> struct StepDraw {
     uint32_t coin[R][2];                               // ... its 16-bit coin ...
     int2 entry[R][2];                                  // ... and the alias entry (load in flight)
 
-    // s_alias: packed (threshold << 16 | alias) copy of the table in shared memory, or unused
-    __device__ __forceinline__ void issue(const TrainParams &P, const uint32_t *s_alias, int sub,
-                                          uint32_t w_lo, uint32_t w_hi, uint32_t q_first)
+    __device__ __forceinline__ void issue(const TrainParams &P, int sub, uint32_t w_lo, uint32_t w_hi,
+                                          uint32_t q_first)
     {
         const uint32_t ctr3 = ((uint32_t)P.epoch << 8) | kStreamSgns;
 #pragma unroll
@@ -210,14 +217,9 @@ template <int G, int KT, bool kSmemAlias> struct StepDraw {
                 coin[r][0] = x.y >> 16;
                 coin[r][1] = x.w >> 16;
             }
-            if constexpr (kSmemAlias) {
-                if (used) entry[r][0].x = (int)s_alias[slot[r][0]];
-                if (second) entry[r][1].x = (int)s_alias[slot[r][1]];
-            } else {
-                // the alias table is read-only for the whole kernel: non-coherent path, L1-cacheable
-                if (used) entry[r][0] = __ldg(reinterpret_cast<const int2 *>(P.alias) + slot[r][0]);
-                if (second) entry[r][1] = __ldg(reinterpret_cast<const int2 *>(P.alias) + slot[r][1]);
-            }
+            // the alias table is read-only for the whole kernel: non-coherent path, L1-cacheable
+            if (used) entry[r][0] = __ldg(reinterpret_cast<const int2 *>(P.alias) + slot[r][0]);
+            if (second) entry[r][1] = __ldg(reinterpret_cast<const int2 *>(P.alias) + slot[r][1]);
         }
     }
 
@@ -227,15 +229,9 @@ template <int G, int KT, bool kSmemAlias> struct StepDraw {
 #pragma unroll
         for (int r = 0; r < R; ++r)
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                if constexpr (kSmemAlias) {
-                    const uint32_t e = (uint32_t)entry[r][j].x;
-                    mine[r][j] = coin[r][j] < (e >> 16) ? slot[r][j] : (int32_t)(e & 0xffffu);
-                } else {
-                    mine[r][j] = coin[r][j] < coin_threshold(__int_as_float(entry[r][j].x)) ? slot[r][j]
-                                                                                         : entry[r][j].y;
-                }
-            }
+            for (int j = 0; j < 2; ++j)
+                mine[r][j] = coin[r][j] < coin_threshold(__int_as_float(entry[r][j].x)) ? slot[r][j]
+                                                                                     : entry[r][j].y;
 #pragma unroll
         for (int x = 0; x < 2 * KT; ++x) {
             const int pair = x / KT, k = x - pair * KT;   // negative k of pair `pair`
@@ -453,103 +449,141 @@ __device__ __forceinline__ void carry_flush(const TrainParams &P, int sub, CtxCa
     carry.xn = carry.yn = -1;
 }
 
-template <int D, int G, int KT, bool kSmemAlias, bool kMerge>
+// ---- the training kernel --------------------------------------------------------------------
+// A worker (lane group of G threads) pulls UNITS -- runs of consecutive walks, planned by
+// gw_sgns_plan -- from a device queue in corpus order and trains each unit's walks one after the
+// other.  Walks come from the token array or, when there is none (kRegen), are regenerated from
+// their Philox counters exactly as gw_walk_uniform draws them: the G threads of the group each
+// generate one of the next G walks into shared memory (9 dependent CSR steps in flight per thread),
+// then the group trains those G walks in order.
+template <int D, int G, int KT, bool kMerge, bool kRegen>
 __global__ void __launch_bounds__(kTrainThreads)
 sgns_train_kernel(const TrainParams P)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     float *s_exp = reinterpret_cast<float *>(s_raw);
-    uint32_t *s_alias = reinterpret_cast<uint32_t *>(s_raw + sizeof(float) * kExpTableSize);
     for (int i = threadIdx.x; i < kExpTableSize; i += blockDim.x) s_exp[i] = P.exp_table[i];
-    if constexpr (kSmemAlias) {
-        // packed copy of the noise table: (16-bit acceptance threshold << 16) | alias (n <= 56000)
-        for (int i = threadIdx.x; i < P.n; i += blockDim.x) {
-            const int2 e = __ldg(reinterpret_cast<const int2 *>(P.alias) + i);
-            s_alias[i] = (coin_threshold(__int_as_float(e.x)) << 16) | (uint32_t)e.y;
-        }
-    }
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int sub = lane & (G - 1);
     const int leader = lane & ~(G - 1);
     const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << leader;
-    const int64_t nchunks = ceil_div<int64_t>(P.W, P.chunk_walks);
+    if (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G >= P.lanes) return;
+    // regenerated walks of this group: [G walks][L tokens]
+    int32_t *s_walks = reinterpret_cast<int32_t *>(s_raw + sizeof(float) * kExpTableSize) +
+                       (size_t)(threadIdx.x - sub) * (size_t)P.L;
+    const unsigned long long num_units = (unsigned long long)__ldg(P.num_units);
     for (;;) {
-        // gensim's job queue: a worker takes the next chunk of the corpus when it finishes one
-        unsigned long long chunk = 0;
-        if (sub == 0) chunk = atomicAdd(P.job_queue, 1ULL);
-        chunk = __shfl_sync(gmask, chunk, leader);
-        if (chunk >= (unsigned long long)(P.streams * P.stream_chunks)) break;
-        // the queue deals chunks from the `streams` corpus slices in turn, so the chunks in flight
-        // are consecutive inside each slice and at most lanes/streams workers share a start node
-        const int64_t slice = (int64_t)(chunk % (unsigned long long)P.streams);
-        const int64_t pos = slice * P.stream_chunks + (int64_t)(chunk / (unsigned long long)P.streams);
-        if (pos >= nchunks) continue;   // ragged last slice
-        const int64_t first = pos * P.chunk_walks;
-        const int64_t last = first + P.chunk_walks < P.W ? first + P.chunk_walks : P.W;
-        // gensim _get_next_alpha at pushed = job*job_walks examples (fp64, unfused, as the oracle);
-        // chunk_walks divides job_walks, so a chunk lies inside one job
-        const int64_t pushed = (first / P.job_walks) * P.job_walks;
-        const double epoch_progress = __ddiv_rn((double)pushed, (double)P.W);
-        const double progress = __ddiv_rn(__dadd_rn((double)P.epoch, epoch_progress), (double)P.epochs);
-        double next_alpha = __dsub_rn(P.alpha0, __dmul_rn(P.alpha_span, progress));
-        if (next_alpha < P.alpha_min) next_alpha = P.alpha_min;
-        const float alpha = (float)next_alpha;
-        for (int64_t w = first; w < last; ++w) {
-            const uint32_t w_lo = (uint32_t)(uint64_t)w, w_hi = (uint32_t)((uint64_t)w >> 32);
-            int32_t prev = -1, cur = __ldg(P.tokens + w);
-            int32_t next = P.L > 1 ? __ldg(P.tokens + P.W + w) : -1;
-            if constexpr (KT > 0) {
-                StepDraw<G, KT, kSmemAlias> draw;
-                draw.issue(P, s_alias, sub, w_lo, w_hi, 0u);
-                CtxCarry<D / G> carry;
-                carry.xn = carry.yn = -1;
-                for (int32_t i = 0; i < P.L && cur >= 0; ++i) {
-                    // token two positions ahead (the next step's right context), loaded early
-                    const int32_t next2 = (i + 2 < P.L && next >= 0) ? __ldg(P.tokens + (int64_t)(i + 2) * P.W + w) : -1;
-                    int32_t tg[2 * KT];
-                    draw.resolve(leader, gmask, tg);
-                    if (prev < 0) {
-#pragma unroll
-                        for (int k = 0; k < KT; ++k) tg[k] = cur;         // absent pair: valid, skipped
+        // gensim's job queue: a worker takes the next unit of the corpus when it finishes one
+        unsigned long long u = 0;
+        if (sub == 0) u = atomicAdd(P.job_queue, 1ULL);
+        u = __shfl_sync(gmask, u, leader);
+        if (u >= num_units) break;
+        const int4 raw = __ldg(reinterpret_cast<const int4 *>(P.units) + u);
+        int64_t w = (int64_t)(((uint64_t)(uint32_t)raw.y << 32) | (uint32_t)raw.x);
+        const int64_t last = w + raw.z;
+        int32_t node = raw.w;   // start node of walk w (regenerated walks)
+        float alpha = 0.0f;
+        int64_t next_job = w;   // the learning rate is set at the first walk and at every job boundary
+        while (w < last) {
+            int nb = 1;
+            if constexpr (kRegen) {
+                nb = last - w < G ? (int)(last - w) : G;
+                int32_t v = node;
+                if (sub < nb) {
+                    const uint64_t ww = (uint64_t)(w + sub);
+                    const int32_t e = (int32_t)(ww / (uint64_t)P.niter);
+                    while (e >= __ldg(P.row_ptr + v + 1)) ++v;   // start node: owner of adjacency entry e
+                    const int32_t v0 = v;
+                    int32_t *out = s_walks + sub * P.L;
+                    out[0] = v;
+                    u32x4 rnd = {0, 0, 0, 0};
+                    for (int32_t st = 1; st < P.L; ++st) {
+                        const int sel = (st - 1) & 3;
+                        if (sel == 0)
+                            rnd = philox4x32_10((uint32_t)ww, (uint32_t)(ww >> 32), (uint32_t)((st - 1) >> 2),
+                                                kStreamWalk, P.wkey0, P.wkey1);
+                        const uint32_t word = sel == 0 ? rnd.x : sel == 1 ? rnd.y : sel == 2 ? rnd.z : rnd.w;
+                        const int32_t b = __ldg(P.row_ptr + v);
+                        const uint32_t deg = (uint32_t)(__ldg(P.row_ptr + v + 1) - b);
+                        v = __ldg(P.col_idx + b + (int32_t)__umulhi(word, deg));
+                        out[st] = v;
                     }
-                    if (next < 0) {
+                    v = v0;
+                }
+                node = __shfl_sync(gmask, v, leader + nb - 1);
+                __syncwarp(gmask);
+            }
+            for (int j = 0; j < nb; ++j, ++w) {
+                if (w >= next_job) {
+                    // gensim _get_next_alpha at pushed = job*job_walks examples (fp64, unfused, as
+                    // the oracle)
+                    const int64_t pushed = (w / P.job_walks) * P.job_walks;
+                    const double epoch_progress = __ddiv_rn((double)pushed, (double)P.W);
+                    const double progress = __ddiv_rn(__dadd_rn((double)P.epoch, epoch_progress), (double)P.epochs);
+                    double next_alpha = __dsub_rn(P.alpha0, __dmul_rn(P.alpha_span, progress));
+                    if (next_alpha < P.alpha_min) next_alpha = P.alpha_min;
+                    alpha = (float)next_alpha;
+                    next_job = pushed + P.job_walks;
+                }
+                const int32_t *s_walk = s_walks + j * P.L;
+                auto token = [&](int32_t i) -> int32_t {
+                    if constexpr (kRegen) return s_walk[i];
+                    else return __ldg(P.tokens + (int64_t)i * P.W + w);
+                };
+                const uint32_t w_lo = (uint32_t)(uint64_t)w, w_hi = (uint32_t)((uint64_t)w >> 32);
+                int32_t prev = -1, cur = token(0);
+                int32_t next = P.L > 1 ? token(1) : -1;
+                if constexpr (KT > 0) {
+                    StepDraw<G, KT> draw;
+                    draw.issue(P, sub, w_lo, w_hi, 0u);
+                    CtxCarry<D / G> carry;
+                    carry.xn = carry.yn = -1;
+                    for (int32_t i = 0; i < P.L && cur >= 0; ++i) {
+                        // token two positions ahead (the next step's right context), loaded early
+                        const int32_t next2 = (i + 2 < P.L && next >= 0) ? token(i + 2) : -1;
+                        int32_t tg[2 * KT];
+                        draw.resolve(leader, gmask, tg);
+                        if (prev < 0) {
 #pragma unroll
-                        for (int k = 0; k < KT; ++k) tg[KT + k] = cur;
-                    }
-                    StepRows<D, G, KT> rows;
-                    if constexpr (kMerge) {
-                        step_gather<D, G, KT>(P, sub, cur, prev, next, tg, rows);
-                        draw.issue(P, s_alias, sub, w_lo, w_hi, 2u * (uint32_t)(i + 1));
-                        step_update_merged<D, G, KT>(P, s_exp, sub, gmask, cur, prev, next, alpha, tg,
-                                                     rows, carry);
-                    } else {
+                            for (int k = 0; k < KT; ++k) tg[k] = cur;         // absent pair: valid, skipped
+                        }
+                        if (next < 0) {
+#pragma unroll
+                            for (int k = 0; k < KT; ++k) tg[KT + k] = cur;
+                        }
+                        StepRows<D, G, KT> rows;
                         step_gather<D, G, KT>(P, sub, cur, prev, next, tg, rows);
                         // the next step's draws (Philox + alias loads) overlap this step's row gathers
-                        draw.issue(P, s_alias, sub, w_lo, w_hi, 2u * (uint32_t)(i + 1));
-                        step_update<D, G, KT>(P, s_exp, sub, gmask, cur, prev, next, alpha, tg, rows);
+                        draw.issue(P, sub, w_lo, w_hi, 2u * (uint32_t)(i + 1));
+                        if constexpr (kMerge)
+                            step_update_merged<D, G, KT>(P, s_exp, sub, gmask, cur, prev, next, alpha, tg,
+                                                         rows, carry);
+                        else
+                            step_update<D, G, KT>(P, s_exp, sub, gmask, cur, prev, next, alpha, tg, rows);
+                        prev = cur;
+                        cur = next;
+                        next = next2;
                     }
-                    prev = cur;
-                    cur = next;
-                    next = next2;
-                }
-                if constexpr (kMerge) carry_flush<D, G>(P, sub, carry);
-            } else {
-                for (int32_t i = 0; i < P.L && cur >= 0; ++i) {
-                    int32_t neg[32];
-                    if (prev >= 0) {
-                        draw_targets<32>(P, P.K, w_lo, w_hi, 2u * i, neg);
-                        pair_sequential<D, G>(P, s_exp, sub, gmask, cur, prev, alpha, neg);
+                    if constexpr (kMerge) carry_flush<D, G>(P, sub, carry);
+                } else {
+                    for (int32_t i = 0; i < P.L && cur >= 0; ++i) {
+                        int32_t neg[32];
+                        if (prev >= 0) {
+                            draw_targets<32>(P, P.K, w_lo, w_hi, 2u * i, neg);
+                            pair_sequential<D, G>(P, s_exp, sub, gmask, cur, prev, alpha, neg);
+                        }
+                        if (next >= 0) {
+                            draw_targets<32>(P, P.K, w_lo, w_hi, 2u * i + 1u, neg);
+                            pair_sequential<D, G>(P, s_exp, sub, gmask, cur, next, alpha, neg);
+                        }
+                        prev = cur;
+                        cur = next;
+                        next = (i + 2 < P.L && cur >= 0) ? token(i + 2) : -1;
                     }
-                    if (next >= 0) {
-                        draw_targets<32>(P, P.K, w_lo, w_hi, 2u * i + 1u, neg);
-                        pair_sequential<D, G>(P, s_exp, sub, gmask, cur, next, alpha, neg);
-                    }
-                    prev = cur;
-                    cur = next;
-                    next = (i + 2 < P.L && cur >= 0) ? __ldg(P.tokens + (int64_t)(i + 2) * P.W + w) : -1;
                 }
             }
+            if constexpr (kRegen) __syncwarp(gmask);   // the group's walks are consumed: slots free
         }
     }
 }
@@ -567,101 +601,167 @@ static void host_exp_table(float *t)
 template <int D, int G, int KT>
 static int launch_train(const TrainParams &P, int64_t lanes, cudaStream_t s)
 {
-    // `lanes` workers of G threads each.  With the noise table in shared memory (n <= 56000) one
-    // CTA per SM holds lanes/num_sms workers (<= 512 threads); otherwise 128-thread CTAs.
-    const bool smem_alias = KT > 0 && P.n <= kSmemAliasMaxN && !P.shared_sm;
-    const int sms = num_sms();
-    int block, blocks;
-    if (lanes * G <= 32) {
-        block = (int)lanes * G;
-        blocks = 1;
-    } else if (smem_alias) {
-        int64_t per_sm = ceil_div<int64_t>(lanes, sms) * G;
-        per_sm = ceil_div<int64_t>(per_sm, 32) * 32;
-        block = (int)(per_sm > kTrainThreads ? kTrainThreads : per_sm);
-        blocks = (int)ceil_div<int64_t>(lanes * G, block);
-        if (blocks > sms) blocks = sms;  // more would not be resident next to a 150+ KB table
-    } else {
-        block = 128;
-        blocks = (int)ceil_div<int64_t>(lanes * G, block);
-    }
-    size_t smem = sizeof(float) * kExpTableSize + (smem_alias ? sizeof(uint32_t) * (size_t)P.n : 0);
+    // `lanes` workers of G threads each in CTAs of 128 threads: the trainings of other replicates,
+    // launched on other streams, share the SMs (independent replicates have independent tables, so
+    // training several at once is what fills the GPU without adding workers per table)
+    const bool regen = P.tokens == nullptr;
+    int block = 128;
+    if (lanes * G < block) block = (int)(ceil_div<int64_t>(lanes * G, 32) * 32);
+    const int blocks = (int)ceil_div<int64_t>(lanes * G, block);
+    const size_t smem = sizeof(float) * kExpTableSize + (regen ? sizeof(int32_t) * (size_t)block * (size_t)P.L : 0);
+    GW_REQUIRE(smem <= 200 * 1024, "gw_sgns_train: walk_length=%d is too long to regenerate walks in the trainer; "
+               "pass the token array", P.L);
     GW_CUDA_OK(cudaMemsetAsync(P.job_queue, 0, sizeof(unsigned long long), s));
     constexpr bool kCanMerge = KT > 0;
-    if (smem_alias) {
-        auto kern = (kCanMerge && P.merge) ? sgns_train_kernel<D, G, KT, true, kCanMerge>
-                                           : sgns_train_kernel<D, G, KT, true, false>;
+    const bool merge = kCanMerge && P.merge;
+    void (*kern)(const TrainParams) =
+        regen ? (merge ? sgns_train_kernel<D, G, KT, kCanMerge, true> : sgns_train_kernel<D, G, KT, false, true>)
+              : (merge ? sgns_train_kernel<D, G, KT, kCanMerge, false> : sgns_train_kernel<D, G, KT, false, false>);
+    if (smem > 48 * 1024)
         GW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<blocks, block, smem, s>>>(P);
-    } else {
-        auto kern = (kCanMerge && P.merge) ? sgns_train_kernel<D, G, KT, false, kCanMerge>
-                                           : sgns_train_kernel<D, G, KT, false, false>;
-        kern<<<blocks, block, smem, s>>>(P);
-    }
+    kern<<<blocks, block, smem, s>>>(P);
     GW_LAUNCH_OK();
     return GW_OK;
 }
 
-// largest divisor of job_walks that is <= want (>= 1)
-static int64_t chunk_divisor(int64_t job_walks, int64_t want)
+// ---- unit planner ------------------------------------------------------------------------------
+__global__ void plan_chunk_kernel(int32_t n, const int32_t *__restrict__ row_ptr, int32_t niter, int64_t W,
+                                  int64_t unit_walks, int64_t nunits, gw_sgns_unit *__restrict__ units,
+                                  int64_t *__restrict__ num_units)
 {
-    if (want >= job_walks) return job_walks;
-    if (want < 1) want = 1;
-    for (int64_t c = want; c > 1; --c)
-        if (job_walks % c == 0) return c;
-    return 1;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *num_units = nunits;
+    if (i >= nunits) return;
+    const int64_t first = i * unit_walks;
+    gw_sgns_unit u;
+    u.first = first;
+    u.count = (int32_t)(first + unit_walks <= W ? unit_walks : W - first);
+    u.node = -1;
+    if (row_ptr) {   // owner of adjacency entry first / niter: last v with row_ptr[v] <= e
+        const int32_t e = (int32_t)(first / niter);
+        int32_t lo = 0, hi = n;   // invariant: row_ptr[lo] <= e < row_ptr[hi]
+        while (hi - lo > 1) {
+            const int32_t mid = (int32_t)(((uint32_t)lo + (uint32_t)hi) >> 1);
+            if (row_ptr[mid] <= e) lo = mid; else hi = mid;
+        }
+        u.node = lo;
+    }
+    units[i] = u;
+}
+
+__global__ void plan_burst_count_kernel(int32_t n, const int32_t *__restrict__ row_ptr, int32_t niter,
+                                        int64_t unit_walks, int64_t *__restrict__ pieces)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const int64_t len = (int64_t)(row_ptr[v + 1] - row_ptr[v]) * niter;
+    pieces[v] = len == 0 ? 0 : ceil_div<int64_t>(len, unit_walks);
+}
+
+__global__ void plan_burst_fill_kernel(int32_t n, const int32_t *__restrict__ row_ptr, int32_t niter,
+                                       const int64_t *__restrict__ offset, const int64_t *__restrict__ total,
+                                       int64_t capacity, gw_sgns_unit *__restrict__ units,
+                                       int64_t *__restrict__ num_units)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v == 0) *num_units = *total <= capacity ? *total : capacity;
+    if (v >= n) return;
+    const int64_t begin = (int64_t)row_ptr[v] * niter, len = (int64_t)(row_ptr[v + 1] - row_ptr[v]) * niter;
+    const int64_t o = offset[v];
+    const int64_t k = (v + 1 < n ? offset[v + 1] : *total) - o;
+    // k near-equal pieces: piece j covers [begin + j*len/k, begin + (j+1)*len/k)
+    for (int64_t j = 0; j < k; ++j) {
+        if (o + j >= capacity) return;
+        const int64_t a = begin + (len * j) / k, b = begin + (len * (j + 1)) / k;
+        gw_sgns_unit u;
+        u.first = a;
+        u.count = (int32_t)(b - a);
+        u.node = v;
+        units[o + j] = u;
+    }
 }
 
 }  // namespace gw
 
-// Default parallel shape.  Fidelity constraints (parity study, profiles/):
-// the Hogwild staleness per table row stays small when the workers stay below ~n/4 and at most
-// ~128 of them train walks that start at the same node; training keeps sweeping the corpus in the
-// reference's node-major order when few slices are active and the chunks in flight inside a slice
-// cover little more than one start node.  Within that: as many workers as fill the GPU.
-extern "C" int gw_sgns_auto_shape(int32_t n, int64_t W, int64_t job_walks, int32_t concurrent,
-                                  int64_t *lanes_out, int64_t *chunk_out, int64_t *streams_out)
+extern "C" int64_t gw_sgns_plan_capacity(int32_t n, int64_t W, int64_t unit_walks, int32_t policy)
 {
-    using namespace gw;
-    GW_REQUIRE(n > 0 && W > 0 && job_walks > 0 && concurrent >= 1 && lanes_out && chunk_out && streams_out,
-               "gw_sgns_auto_shape: bad arguments");
-    // 128 workers (512 threads at d = 8) per SM are resident at the kernel's register budget; the
-    // trainings that run at once share them (all co-resident: measured optimum)
-    int64_t lanes = (int64_t)num_sms() * 128 / concurrent;
-    if (lanes > n / 4) lanes = n / 4;
-    if (lanes < 1) lanes = 1;
-    const int64_t chunk = chunk_divisor(job_walks, 8);
-    const int64_t nchunks = ceil_div<int64_t>(W, chunk);
-    if (lanes > nchunks) lanes = nchunks;
-    int64_t streams = ceil_div<int64_t>(lanes, 128);
-    const int64_t max_streams = n / 50 > 0 ? n / 50 : 1;
-    if (streams > max_streams) streams = max_streams;
-    *lanes_out = lanes;
-    *chunk_out = chunk;
-    *streams_out = streams;
-    return GW_OK;
+    if (unit_walks < 1) unit_walks = 1;
+    const int64_t chunks = (W + unit_walks - 1) / unit_walks;
+    return policy == GW_PLAN_BURST ? chunks + (int64_t)n : chunks;
 }
 
-extern "C" int gw_sgns_train(int32_t n, int32_t d, const int32_t *tokens, int64_t W, int32_t L,
-                             int32_t window, int32_t K, int32_t epochs, int32_t epoch_begin,
-                             int32_t epoch_end, double alpha0, double alpha_min, int64_t job_walks,
-                             int64_t chunk_walks, int64_t streams, const gw_alias_entry *alias_table,
-                             float *syn0, float *syn1neg, uint64_t seed, int64_t lanes,
-                             int32_t flags, gw_stream_t stream)
+extern "C" int gw_sgns_plan(int32_t n, const int32_t *row_ptr, int32_t niter, int64_t W, int64_t unit_walks,
+                            int32_t policy, gw_sgns_unit *units, int64_t capacity, int64_t *num_units,
+                            gw_stream_t stream)
 {
     using namespace gw;
     cudaStream_t s = (cudaStream_t)stream;
-    GW_REQUIRE(n > 0 && tokens && alias_table && syn0 && syn1neg, "gw_sgns_train: null argument");
+    GW_REQUIRE(units && num_units && W > 0 && unit_walks >= 1 && unit_walks < ((int64_t)1 << 31),
+               "gw_sgns_plan: bad arguments");
+    GW_REQUIRE(capacity >= gw_sgns_plan_capacity(n, W, unit_walks, policy),
+               "gw_sgns_plan: capacity %lld < gw_sgns_plan_capacity()", (long long)capacity);
+    if (policy == GW_PLAN_CHUNK) {
+        const int64_t nunits = ceil_div<int64_t>(W, unit_walks);
+        plan_chunk_kernel<<<(unsigned)ceil_div<int64_t>(nunits, 256), 256, 0, s>>>(n, row_ptr, niter, W, unit_walks,
+                                                                                 nunits, units, num_units);
+        GW_LAUNCH_OK();
+        return GW_OK;
+    }
+    GW_REQUIRE(policy == GW_PLAN_BURST, "gw_sgns_plan: unknown policy %d", policy);
+    GW_REQUIRE(row_ptr && n > 0 && niter > 0, "gw_sgns_plan: the burst policy needs the graph");
+    Temp pieces, total;
+    GW_CUDA_OK(pieces.alloc(sizeof(int64_t) * (size_t)n, s));
+    GW_CUDA_OK(total.alloc(sizeof(int64_t), s));
+    const unsigned grid = (unsigned)ceil_div<int64_t>(n, 256);
+    plan_burst_count_kernel<<<grid, 256, 0, s>>>(n, row_ptr, niter, unit_walks, pieces.as<int64_t>());
+    GW_LAUNCH_OK();
+    GW_TRY(scan_exclusive_i64(pieces.as<int64_t>(), pieces.as<int64_t>(), n, total.as<int64_t>(), s));
+    plan_burst_fill_kernel<<<grid, 256, 0, s>>>(n, row_ptr, niter, pieces.as<int64_t>(), total.as<int64_t>(),
+                                                capacity, units, num_units);
+    GW_LAUNCH_OK();
+    return GW_OK;
+}
+
+// Default parallel shape: a function of the network alone -- never of how
+// many trainings share the GPU or of how many GPUs the replicates are spread over, so that a seed
+// gives the same statistics on 1 and on 8 GPUs.
+extern "C" int gw_sgns_auto_shape(int32_t n, int64_t W, int64_t job_walks, int64_t *lanes_out,
+                                  int64_t *unit_walks_out, int32_t *policy_out)
+{
+    using namespace gw;
+    GW_REQUIRE(n > 0 && W > 0 && job_walks > 0 && lanes_out && unit_walks_out && policy_out,
+               "gw_sgns_auto_shape: bad arguments");
+    int64_t lanes = kAutoLanesMax;
+    if (lanes > n / kAutoRowsPerLane) lanes = n / kAutoRowsPerLane;
+    if (lanes < 1) lanes = 1;
+    const int64_t unit = kAutoUnitWalks;
+    const int64_t nunits = ceil_div<int64_t>(W, unit);
+    if (lanes > nunits) lanes = nunits;
+    *lanes_out = lanes;
+    *unit_walks_out = unit;
+    *policy_out = kAutoPolicy;
+    return GW_OK;
+}
+
+extern "C" int gw_sgns_train(int32_t n, int32_t d, const int32_t *tokens, const int32_t *row_ptr,
+                             const int32_t *col_idx, int32_t niter, uint64_t walk_seed, int64_t W, int32_t L,
+                             int32_t window, int32_t K, int32_t epochs, int32_t epoch_begin,
+                             int32_t epoch_end, double alpha0, double alpha_min, int64_t job_walks,
+                             const gw_sgns_unit *units, const int64_t *num_units,
+                             const gw_alias_entry *alias_table, float *syn0, float *syn1neg,
+                             uint64_t seed, int64_t lanes, int32_t flags, gw_stream_t stream)
+{
+    using namespace gw;
+    cudaStream_t s = (cudaStream_t)stream;
+    GW_REQUIRE(n > 0 && alias_table && syn0 && syn1neg && units && num_units, "gw_sgns_train: null argument");
+    GW_REQUIRE(tokens || (row_ptr && col_idx && niter > 0),
+               "gw_sgns_train: pass the token array, or the graph (row_ptr, col_idx, niter) to regenerate the walks");
     GW_REQUIRE(W > 0 && L >= 1 && L <= 4096, "gw_sgns_train: W=%lld L=%d out of range", (long long)W, L);
     GW_REQUIRE(K >= 0 && K <= 32, "gw_sgns_train: negative=%d out of range [0,32]", K);
     GW_REQUIRE(epochs >= 1 && epochs <= 65535 && epoch_begin >= 0 && epoch_begin <= epoch_end &&
                    epoch_end <= epochs,
                "gw_sgns_train: epochs=%d [%d,%d) invalid", epochs, epoch_begin, epoch_end);
-    GW_REQUIRE(job_walks >= 1 && lanes >= 0 && chunk_walks >= 0 && streams >= 0,
-               "gw_sgns_train: job_walks/chunk_walks/streams/lanes invalid");
-    GW_REQUIRE(chunk_walks == 0 || (chunk_walks <= job_walks && job_walks % chunk_walks == 0),
-               "gw_sgns_train: chunk_walks=%lld must divide job_walks=%lld", (long long)chunk_walks,
-               (long long)job_walks);
+    GW_REQUIRE(job_walks >= 1 && lanes >= 1, "gw_sgns_train: job_walks/lanes invalid");
     if (window != 1) {
         set_error("gw_sgns_train: window=%d is not implemented (GeneWalk uses window=1)", window);
         return GW_ERR_UNSUPPORTED;
@@ -670,16 +770,9 @@ extern "C" int gw_sgns_train(int32_t n, int32_t d, const int32_t *tokens, int64_
         set_error("gw_sgns_train: vector_size=%d is not implemented (8, 16, 32, 64, 128)", d);
         return GW_ERR_UNSUPPORTED;
     }
-    GW_REQUIRE((reinterpret_cast<uintptr_t>(syn0) & 15) == 0 && (reinterpret_cast<uintptr_t>(syn1neg) & 15) == 0,
-               "gw_sgns_train: tables must be 16-byte aligned");
-    int64_t auto_lanes = 0, auto_chunk = 0, auto_streams = 0;
-    GW_TRY(gw_sgns_auto_shape(n, W, job_walks, 1, &auto_lanes, &auto_chunk, &auto_streams));
-    if (lanes == 0) lanes = auto_lanes;
-    if (chunk_walks == 0) chunk_walks = lanes == 1 ? job_walks : auto_chunk;
-    const int64_t nchunks = ceil_div<int64_t>(W, chunk_walks);
-    if (lanes > nchunks) lanes = nchunks;
-    if (streams == 0) streams = lanes == 1 ? 1 : (auto_streams < lanes ? auto_streams : lanes);
-    if (streams > nchunks) streams = nchunks;
+    GW_REQUIRE((reinterpret_cast<uintptr_t>(syn0) & 15) == 0 && (reinterpret_cast<uintptr_t>(syn1neg) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(units) & 15) == 0,
+               "gw_sgns_train: tables and units must be 16-byte aligned");
     float h_exp[kExpTableSize];
     host_exp_table(h_exp);
     Temp d_exp, d_queue;
@@ -688,18 +781,13 @@ extern "C" int gw_sgns_train(int32_t n, int32_t d, const int32_t *tokens, int64_
     // pageable source: the copy is staged before the call returns, so the stack buffer is safe
     GW_CUDA_OK(cudaMemcpyAsync(d_exp.ptr, h_exp, sizeof h_exp, cudaMemcpyHostToDevice, s));
     TrainParams P;
-    P.tokens = tokens; P.W = W; P.L = L; P.n = n; P.K = K; P.epochs = epochs; P.epoch = 0;
+    P.tokens = tokens; P.row_ptr = row_ptr; P.col_idx = col_idx; P.niter = niter;
+    P.wkey0 = (uint32_t)walk_seed; P.wkey1 = (uint32_t)(walk_seed >> 32);
+    P.W = W; P.L = L; P.n = n; P.K = K; P.epochs = epochs; P.epoch = 0;
     P.alpha0 = alpha0; P.alpha_span = alpha0 - alpha_min; P.alpha_min = alpha_min;
-    P.job_walks = job_walks; P.chunk_walks = chunk_walks;
-    P.streams = streams; P.stream_chunks = ceil_div<int64_t>(nchunks, streams);
-    P.shared_sm = (flags & GW_SGNS_SHARED_SM) ? 1 : 0;
-    // per-pair reductions in gensim's order when sequential or when asked for
-    // Holding an update back for two steps adds to the Hogwild staleness of the row in proportion to
-    // workers / rows: measured neutral at 3157 workers on 38000 rows (KS 0.004 either way against a
-    // 512-worker run), visible at 575 workers on 2300 rows (KS against the sequential gensim-faithful
-    // oracle 0.050 vs 0.032).  Default: merged only where it is neutral.
-    P.merge = (flags & GW_SGNS_MERGED) ? 1 : (flags & GW_SGNS_PER_PAIR) ? 0
-              : (lanes > 1 && lanes * 12 <= (int64_t)n ? 1 : 0);
+    P.job_walks = job_walks; P.units = units; P.num_units = num_units; P.lanes = lanes;
+    // per-pair reductions in gensim's order unless the merged order is asked for
+    P.merge = (flags & GW_SGNS_MERGED) ? 1 : 0;
     P.job_queue = d_queue.as<unsigned long long>();
     P.alias = alias_table; P.exp_table = d_exp.as<float>();
     P.syn0 = syn0; P.syn1neg = syn1neg; P.key0 = (uint32_t)seed; P.key1 = (uint32_t)(seed >> 32);

@@ -45,27 +45,56 @@ def _csr_of(graph):
 
 
 class WalkCorpus(Sequence):
-    """Lazy list-of-walks view over the device token array.
+    """Lazy list-of-walks view.
 
     Index ``i`` is the walk's position in the reference's serial corpus (node-major: node v owns
-    ``niter*len(graph[v])`` consecutive walks, deepwalk.py:67-70,197); the device stores walks in
-    slot order (see gw_walk_uniform) and position-major (``tokens[k, p]`` = k-th node of slot p).
+    ``niter*len(graph[v])`` consecutive walks, deepwalk.py:67-70,197).  Walks are a pure function
+    of (graph, seed, walk id) -- gw_walk_uniform draws walk w from its own Philox counter -- so the
+    corpus is not stored: slices are generated on the device when they are read, the trainer
+    regenerates every walk in its own registers, and ``tokens`` (the full position-major
+    ``[L, W]`` int32 device array, 6 GB at human scale) is only materialised when asked for.
+    With ``stride > 0`` the storage order is iteration-major (see gw_walk_uniform).
     """
 
-    def __init__(self, csr, tokens, niter, stride):
+    def __init__(self, csr, niter, walk_length, seed, stride=0):
         self.csr = csr
-        self.tokens = tokens          # torch int32 [L, W] on the device (or numpy after pickling)
         self.niter = int(niter)
+        self.wl = int(walk_length)
+        self.seed = int(seed)
         self.stride = int(stride)
         self.A = csr.nnz
+        self._tokens = None
         self._inv = pow(self.stride, -1, self.A) if (self.A > 1 and self.stride > 0) else 0
 
     def __len__(self):
-        return int(self.tokens.shape[1])
+        return self.niter * self.A
 
     @property
     def walk_length(self):
-        return int(self.tokens.shape[0])
+        return self.wl
+
+    def generate(self, slot_begin, slot_end):
+        """Device int32 tensor [L, slot_end - slot_begin] of the walks in those storage slots."""
+        import torch
+        csr = self.csr.to_device()
+        out = torch.empty((self.wl, int(slot_end - slot_begin)), dtype=torch.int32,
+                          device=csr.d_row_ptr.device)
+        if slot_end > slot_begin:
+            _lib.call('gw_walk_uniform', csr.n, self.A, _lib.ptr(csr.d_row_ptr), _lib.ptr(csr.d_col_idx),
+                      self.niter, self.wl, self.seed, self.stride, int(slot_begin), int(slot_end),
+                      _lib.ptr(out), _lib.stream_ptr())
+        return out
+
+    @property
+    def tokens(self):
+        """The whole corpus as a device tensor [L, W] (materialised on first access)."""
+        if self._tokens is None:
+            self._tokens = self.generate(0, len(self))
+        return self._tokens
+
+    def release(self):
+        """Drop a materialised token array (the walks themselves stay reproducible)."""
+        self._tokens = None
 
     def slots_of(self, idx):
         idx = np.asarray(idx, dtype=np.int64)
@@ -81,8 +110,14 @@ class WalkCorpus(Sequence):
 
     def _fetch(self, idx):
         slots = self.slots_of(idx)
-        if isinstance(self.tokens, np.ndarray):
-            return self.tokens[:, slots].T
+        if isinstance(self._tokens, np.ndarray):
+            return self._tokens[:, slots].T
+        if len(slots) == 0:
+            return np.zeros((0, self.wl), dtype=np.int32)
+        if self._tokens is None and np.all(np.diff(slots) == 1):   # a contiguous run: generate it
+            return self.generate(int(slots[0]), int(slots[-1]) + 1).t().cpu().numpy()
+        if self._tokens is None and len(slots) == 1:
+            return self.generate(int(slots[0]), int(slots[0]) + 1).t().cpu().numpy()
         import torch
         sl = torch.as_tensor(slots, device=self.tokens.device)
         return self.tokens.index_select(1, sl).t().cpu().numpy()
@@ -110,8 +145,8 @@ class WalkCorpus(Sequence):
 
     def __getstate__(self):
         st = dict(self.__dict__)
-        if not isinstance(self.tokens, np.ndarray):
-            st['tokens'] = self.tokens.cpu().numpy()
+        if st['_tokens'] is not None and not isinstance(st['_tokens'], np.ndarray):
+            st['_tokens'] = st['_tokens'].cpu().numpy()
         self.csr.to_host()
         st['csr'] = GraphCSR(self.csr.nodes, self.csr.row_ptr, self.csr.col_idx)
         return st
@@ -158,13 +193,15 @@ class DeepWalk(object):
             self._csr = _csr_of(self.graph)
         return self._csr
 
-    def get_walks(self, workers=1, stride=None):
+    def get_walks(self, workers=1, stride=None, materialize=False):
         """Generates walks (sentences) sampled by an (unbiased) random walk over the graph.
 
         ``workers`` is accepted for API compatibility (the GPU runs one thread per walk).
         ``stride`` selects the storage order (0, default: the reference's node-major corpus order,
         which is also the order the learning-rate schedule of ``word2vec`` refers to; s > 0:
         iteration-major with adjacency entries permuted by a stride coprime to A).
+        The walks are a lazy sequence (see ``WalkCorpus``): nothing is stored unless
+        ``materialize`` is set or ``self.walks.tokens`` is read.
         """
         import torch
         _lib.require_cuda()
@@ -175,30 +212,30 @@ class DeepWalk(object):
         seed = self.seed if self.seed is not None else random.getrandbits(64)
         self._walk_seed = int(seed) & (2 ** 64 - 1)
         csr = self._get_csr().to_device()
-        A = csr.nnz
-        if A == 0:
+        if csr.nnz == 0:
             self.walks = []
             return
-        W = int(self.niter) * A
-        stride = 0 if stride is None else int(stride)
-        tokens = torch.empty((int(self.wl), W), dtype=torch.int32, device=csr.d_row_ptr.device)
-        _lib.call('gw_walk_uniform', csr.n, A, _lib.ptr(csr.d_row_ptr), _lib.ptr(csr.d_col_idx),
-                  int(self.niter), int(self.wl), self._walk_seed, stride, 0, W, _lib.ptr(tokens),
-                  _lib.stream_ptr())
-        self.walks = WalkCorpus(csr, tokens, self.niter, stride)
+        self.walks = WalkCorpus(csr, self.niter, self.wl, self._walk_seed, 0 if stride is None else int(stride))
+        if materialize:
+            self.walks.tokens
         end = time.time()
         self.timings['get_walks_enqueue_s'] = end - start
         logger.info('Running random walks done in %.2fs' % (end - start))
 
     # ------------------------------------------------------------------------------------------
     def _device_corpus(self):
-        """(csr-like node list, n, tokens [L, W] device tensor) of ``self.walks``."""
+        """(node list, n, tokens [L, W] device tensor or None, WalkCorpus or None) of ``self.walks``.
+        tokens is None when the trainer can regenerate the walks itself (a lazy corpus in the
+        reference's order)."""
         import torch
         if isinstance(self.walks, WalkCorpus):
-            tok = self.walks.tokens
+            wc = self.walks
+            if wc.stride == 0 and wc._tokens is None:
+                return wc.csr.nodes, wc.csr.n, None, wc
+            tok = wc.tokens
             if isinstance(tok, np.ndarray):
                 tok = torch.from_numpy(tok).cuda()
-            return self.walks.csr.nodes, self.walks.csr.n, tok
+            return wc.csr.nodes, wc.csr.n, tok, (wc if wc.stride == 0 else None)
         # a plain list of lists of labels (what the reference stores): encode, pad ragged with -1
         walks = list(self.walks)
         if not walks:
@@ -213,7 +250,7 @@ class DeepWalk(object):
                     i = index[t] = len(nodes)
                     nodes.append(t)
                 arr[k, p] = i
-        return nodes, len(nodes), torch.from_numpy(arr).cuda()
+        return nodes, len(nodes), torch.from_numpy(arr).cuda(), None
 
     def word2vec(self, sg=1, vector_size=8, window=1, min_count=1, negative=5,
                  workers=1, sample=0, **kwargs):
@@ -223,13 +260,10 @@ class DeepWalk(object):
         defaults can be overridden by keyword: ``epochs`` (5), ``alpha`` (0.025), ``min_alpha``
         (0.0001), ``seed`` (1, weight init), ``ns_exponent`` (0.75), ``batch_words`` (10000),
         ``hs`` (0).  GPU-only knobs: ``lanes`` (number of concurrent workers, the analogue of
-        gensim's ``workers``: each trains one 1000-walk job at a time, taken from a queue in corpus
-        order; 0 = library default, 1 = sequential), ``chunk_walks`` (walks a worker takes from
-        the queue at a time; must divide the job size; 0 = library default), ``streams`` (corpus
-        slices the queue deals chunks from in turn; 0 = library default), ``concurrent`` (number of
-        trainings the caller runs at once on this GPU on different CUDA streams: they share the
-        GPU's resident workers and leave the SMs' shared memory to each other; default 1),
-        ``reductions`` ('auto' | 'per_pair' | 'merged': see ``gw_sgns_flags`` in
+        gensim's ``workers``; 0 = library default, a function of the network only; 1 =
+        sequential), ``unit_walks`` and ``policy`` ('chunk' | 'burst': how the corpus is cut into
+        the units the workers take from the queue, see ``gw_sgns_plan``; 0 / None = library
+        default), ``reductions`` ('per_pair' | 'merged': see ``gw_sgns_flags`` in
         include/genewalk_b200.h), ``wait`` (False: only enqueue the training on the current CUDA
         stream; ``finish_word2vec()`` then downloads the vectors) and ``sgns_seed`` (Philox key of
         the negative draws).
@@ -244,11 +278,9 @@ class DeepWalk(object):
         batch_words = int(kwargs.pop('batch_words', 10000))
         hs = int(kwargs.pop('hs', 0))
         lanes = int(kwargs.pop('lanes', 0))
-        chunk_walks = int(kwargs.pop('chunk_walks', 0))
-        streams = int(kwargs.pop('streams', 0))
-        concurrent = int(kwargs.pop('concurrent', 1))
-        shared_sm = bool(kwargs.pop('shared_sm', concurrent > 1))
-        reductions = kwargs.pop('reductions', 'auto')
+        unit_walks = int(kwargs.pop('unit_walks', 0))
+        policy = kwargs.pop('policy', None)
+        reductions = kwargs.pop('reductions', 'per_pair')
         kwargs_async = not bool(kwargs.pop('wait', True))
         sgns_seed = kwargs.pop('sgns_seed', None)
         if kwargs:
@@ -272,9 +304,8 @@ class DeepWalk(object):
         self._pending = self.train_device(vector_size=vector_size, negative=negative, epochs=epochs,
                                           alpha=alpha, min_alpha=min_alpha, init_seed=init_seed,
                                           ns_exponent=ns_exponent, batch_words=batch_words,
-                                          lanes=lanes, chunk_walks=chunk_walks, streams=streams,
-                                          shared_sm=shared_sm, reductions=reductions, concurrent=concurrent,
-                                          sgns_seed=sgns_seed)
+                                          lanes=lanes, unit_walks=unit_walks, policy=policy,
+                                          reductions=reductions, sgns_seed=sgns_seed)
         if kwargs_async:
             return          # training is enqueued; finish_word2vec() downloads the vectors
         self.finish_word2vec()
@@ -287,6 +318,7 @@ class DeepWalk(object):
         ``self.model`` (the only host synchronisation of a replicate)."""
         dv = self._pending
         self._pending = None
+        self.train_shape = {k: dv[k] for k in ('lanes', 'unit_walks', 'policy', 'regenerated')}
         nodes = dv['nodes']
         nv = int(dv['n_vocab'].item())
         order = dv['node_of_rank'][:nv].long()
@@ -300,18 +332,22 @@ class DeepWalk(object):
         return self.model
 
     def train_device(self, vector_size=8, negative=5, epochs=5, alpha=0.025, min_alpha=0.0001,
-                     init_seed=1, ns_exponent=0.75, batch_words=10000, lanes=0, chunk_walks=0,
-                     streams=0, shared_sm=None, reductions='auto', concurrent=1, sgns_seed=None,
-                     epoch_hook=None):
+                     init_seed=1, ns_exponent=0.75, batch_words=10000, lanes=0, unit_walks=0,
+                     policy=None, reductions='per_pair', sgns_seed=None, epoch_hook=None):
         """Enqueue vocabulary, alias table, init and the SGNS epochs on the current stream and
         return the device tensors (no host synchronisation).  ``epoch_hook(ep, when)`` is called
         with when in {'before', 'after'} around every epoch's launch (bench.py records CUDA
         events there)."""
+        import ctypes
         import torch
-        nodes, n, tokens = self._device_corpus()
-        L, W = int(tokens.shape[0]), int(tokens.shape[1])
+        nodes, n, tokens, wc = self._device_corpus()
+        if tokens is not None:
+            L, W = int(tokens.shape[0]), int(tokens.shape[1])
+            dev = tokens.device
+        else:
+            L, W = wc.wl, len(wc)
+            dev = wc.csr.to_device().d_row_ptr.device
         d = int(vector_size)
-        dev = tokens.device
         st = _lib.stream_ptr()
         if sgns_seed is None:
             sgns_seed = (getattr(self, '_walk_seed', 0) ^ 0x5DEECE66D5DEECE6) & (2 ** 64 - 1)
@@ -324,50 +360,79 @@ class DeepWalk(object):
         syn1neg = torch.empty((n, d), dtype=torch.float32, device=dev)
         # gensim init_weights: rows of default_rng(seed).random((V, d), float32); V <= n and the
         # generator fills row-major, so the first V rows of an (n, d) draw are the (V, d) draw
-        rng = np.random.default_rng(seed=init_seed)
-        rows = rng.random((n, d), dtype=np.float32)
-        rows *= 2.0
-        rows -= 1.0
-        rows /= d
-        rng_rows = torch.from_numpy(rows).to(dev)
-        _lib.call('gw_count_tokens', _lib.ptr(tokens), L * W, n, _lib.ptr(counts), st)
+        rng_rows = _init_rows(n, d, init_seed, dev)
+        graph = wc.csr.to_device() if wc is not None else None
+        if tokens is not None:
+            _lib.call('gw_count_tokens', _lib.ptr(tokens), L * W, n, _lib.ptr(counts), st)
+        else:
+            _lib.call('gw_walk_count', n, graph.nnz, _lib.ptr(graph.d_row_ptr), _lib.ptr(graph.d_col_idx),
+                      wc.niter, L, wc.seed, _lib.ptr(counts), st)
         _lib.call('gw_vocab_rank', n, _lib.ptr(counts), _lib.ptr(rank_of_node),
                   _lib.ptr(node_of_rank), _lib.ptr(n_vocab), st)
         _lib.call('gw_alias_build', n, _lib.ptr(counts), float(ns_exponent), _lib.ptr(alias), st)
         _lib.call('gw_sgns_init', n, d, _lib.ptr(rank_of_node), _lib.ptr(rng_rows), _lib.ptr(syn0),
                   _lib.ptr(syn1neg), st)
         job_walks = max(1, int(batch_words) // max(L, 1))
-        if int(lanes) == 0 or int(chunk_walks) == 0 or int(streams) == 0:
-            import ctypes
-            a_l, a_c, a_s = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
-            _lib.call('gw_sgns_auto_shape', n, W, job_walks, max(1, int(concurrent)),
-                      ctypes.byref(a_l), ctypes.byref(a_c),
-                      ctypes.byref(a_s))
-            if int(lanes) == 0:
-                lanes = a_l.value
-            if int(chunk_walks) == 0:
-                chunk_walks = job_walks if int(lanes) == 1 else a_c.value
-            if int(streams) == 0:
-                streams = 1 if int(lanes) == 1 else min(a_s.value, int(lanes))
-        if shared_sm is None:
-            shared_sm = int(concurrent) > 1
-        flags = (1 if shared_sm else 0) | {'auto': 0, 'per_pair': 2, 'merged': 4}[reductions]
+        a_l, a_u, a_p = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int32(0)
+        _lib.call('gw_sgns_auto_shape', n, W, job_walks, ctypes.byref(a_l), ctypes.byref(a_u),
+                  ctypes.byref(a_p))
+        if int(lanes) == 0:
+            lanes = a_l.value
+        if int(unit_walks) == 0:
+            unit_walks = a_u.value
+        policy_id = a_p.value if policy is None else {'chunk': 0, 'burst': 1}[policy]
+        if graph is None:
+            policy_id = 0          # no graph behind the corpus: plain chunks
+        lib = _lib.load()
+        cap = int(lib.gw_sgns_plan_capacity(n, W, int(unit_walks), policy_id))
+        units = torch.empty((cap, 2), dtype=torch.int64, device=dev)    # gw_sgns_unit[cap]
+        num_units = torch.zeros(1, dtype=torch.int64, device=dev)
+        _lib.call('gw_sgns_plan', n, _lib.ptr(graph.d_row_ptr) if graph is not None else None,
+                  wc.niter if wc is not None else 1, W, int(unit_walks), policy_id, _lib.ptr(units), cap,
+                  _lib.ptr(num_units), st)
+        flags = {'per_pair': 0, 'merged': 4}[reductions]
+        regen = tokens is None
         for ep in range(int(epochs)):
             if epoch_hook is not None:
                 epoch_hook(ep, 'before')
-            _lib.call('gw_sgns_train', n, d, _lib.ptr(tokens), W, L, 1, int(negative), int(epochs),
-                      ep, ep + 1, float(alpha), float(min_alpha), job_walks, int(chunk_walks),
-                      int(streams), _lib.ptr(alias),
-                      _lib.ptr(syn0), _lib.ptr(syn1neg), int(sgns_seed), int(lanes),
-                      flags, st)
+            _lib.call('gw_sgns_train', n, d, None if regen else _lib.ptr(tokens),
+                      _lib.ptr(graph.d_row_ptr) if regen else None,
+                      _lib.ptr(graph.d_col_idx) if regen else None,
+                      wc.niter if regen else 0, wc.seed if regen else 0, W, L, 1, int(negative),
+                      int(epochs), ep, ep + 1, float(alpha), float(min_alpha), job_walks,
+                      _lib.ptr(units), _lib.ptr(num_units), _lib.ptr(alias),
+                      _lib.ptr(syn0), _lib.ptr(syn1neg), int(sgns_seed), int(lanes), flags, st)
             if epoch_hook is not None:
                 epoch_hook(ep, 'after')
         return {'nodes': nodes, 'n': n, 'W': W, 'L': L, 'syn0': syn0, 'syn1neg': syn1neg,
                 'counts': counts, 'rank_of_node': rank_of_node, 'node_of_rank': node_of_rank,
-                'n_vocab': n_vocab, 'alias': alias, 'rng_rows': rng_rows,
-                'lanes': int(lanes), 'chunk_walks': int(chunk_walks), 'streams': int(streams),
-                'job_walks': job_walks,
-                'h2d_bytes': rows.nbytes}
+                'n_vocab': n_vocab, 'alias': alias, 'rng_rows': rng_rows, 'units': units,
+                'num_units': num_units, 'lanes': int(lanes), 'unit_walks': int(unit_walks),
+                'policy': ('chunk', 'burst')[policy_id], 'job_walks': job_walks,
+                'regenerated': regen, 'h2d_bytes': n * d * 4}
+
+
+_INIT_ROWS = {}
+
+
+def _init_rows(n, d, seed, dev):
+    """Device copy of gensim's init_weights rows, (default_rng(seed).random((n, d), f32)*2-1)/d;
+    every replicate of a run uses the same matrix (gensim's seed is always 1 in GeneWalk,
+    deepwalk.py:135-139), so it is generated and uploaded once per (n, d, seed, device)."""
+    import torch
+    key = (int(n), int(d), int(seed), str(dev))
+    t = _INIT_ROWS.get(key)
+    if t is None:
+        rng = np.random.default_rng(seed=seed)
+        rows = rng.random((n, d), dtype=np.float32)
+        rows *= 2.0
+        rows -= 1.0
+        rows /= d
+        if len(_INIT_ROWS) >= 8:
+            _INIT_ROWS.clear()
+        t = _INIT_ROWS[key] = torch.from_numpy(rows).to(dev)
+        torch.cuda.current_stream().synchronize()   # other streams will read it
+    return t
 
 
 # ---------------------------------------------------------------------------------------------

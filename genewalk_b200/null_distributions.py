@@ -129,7 +129,15 @@ def get_null_distributions(rg, nv):
         idx = csr.index
         ids = np.fromiter((idx[k] for k in nv.index_to_key), dtype=np.int64,
                           count=len(nv.index_to_key))
-    full[np.asarray(ids, dtype=np.int64)] = nv.vectors
+    ids = np.asarray(ids, dtype=np.int64)
+    full[ids] = nv.vectors
+    # a node that has neighbours but no vector: the reference's nv.distances raises KeyError
+    # (null_distributions.py:46); zero rows here would put NaN similarities into the null
+    have = torch.zeros(csr.n, dtype=torch.bool, device=dev)
+    have[torch.from_numpy(ids).to(dev)] = True
+    lost = torch.nonzero(~have & (csr.d_row_ptr[1:] > csr.d_row_ptr[:-1])).reshape(-1)
+    if lost.numel() > 0:
+        raise KeyError("Key '%s' not present" % (csr.nodes[int(lost[0])],))
     vec = torch.from_numpy(full).to(dev)
     sims = torch.empty(csr.nnz, dtype=torch.float32, device=dev)
     cnt = ctypes.c_int64(0)

@@ -131,25 +131,19 @@ def exchange_results(local_sims, local_null, nreps_graph, nreps_null, m, device,
 # ---------------------------------------------------------------------------------------------
 # the replicate bodies
 # ---------------------------------------------------------------------------------------------
-DEFAULT_CONCURRENT = 6   # replicates trained at once per GPU (independent tables: see DESIGN 4.2)
+DEFAULT_CONCURRENT = 24   # replicates in flight per GPU: all units of an nreps = 10 + 10 run
 
 
-def fit_concurrent(requested, nnz, niter=100, walk_length=10):
-    """Replicates to run at once: ``requested``, capped so that their walk corpora (the only large
-    per-replicate allocation: niter * nnz walks of walk_length int32 tokens) fit the free HBM."""
+def fit_concurrent(requested, n, vector_size=8):
+    """Replicates to run at once: ``requested``, capped by the free HBM.  The walks are never stored
+    (the trainer regenerates them), so a replicate in flight holds only its tables, vocabulary,
+    noise table, unit plan and (null replicates) its randomized graph: a few MB at human scale.
+    The number in flight does NOT change any replicate's result: every training gets the same
+    number of workers whatever shares the GPU with it (gw_sgns_auto_shape)."""
     import torch
-    # 1.6x: a randomized network has up to ~1.3x the adjacency entries of the real one (parallel
-    # edges of the MultiGraph become distinct neighbours), and a stream keeps its previous, smaller
-    # corpus buffer cached next to the new one
-    per_replicate = int(1.6 * 4 * walk_length * niter * max(int(nnz), 1)) + (256 << 20)
+    per_replicate = int(n) * (2 * 4 * int(vector_size) + 64) + (64 << 20)
     free, _ = torch.cuda.mem_get_info()
-    if int(0.85 * free) < int(requested) * per_replicate:
-        # blocks torch's allocator caches for other streams cannot serve ours: hand them back now,
-        # while the device is idle (an allocation that does not fit later would make the allocator
-        # free them in the middle of the run, which waits for all streams to drain)
-        torch.cuda.empty_cache()
-        free, _ = torch.cuda.mem_get_info()
-    return max(1, min(int(requested), int(0.85 * free) // per_replicate))
+    return max(1, min(int(requested), int(0.8 * free) // per_replicate))
 
 
 def real_replicate(csr, base_seed, rep, dim_rep=8, walk_length=10, niter=100, wait=True, **w2v):
@@ -219,7 +213,7 @@ def _side_streams(count):
     return pool[:count]
 
 
-def preload_kernels(dim_rep=8, concurrent=1, **w2v):
+def preload_kernels(dim_rep=8, **w2v):
     """Launch every kernel of a real and a null replicate once, on a 12-node network, while the
     device is idle.  CUDA loads a kernel at its first launch and that load waits until ALL streams
     have drained: with replicates in flight on several streams, the first randomized network and
@@ -227,19 +221,19 @@ def preload_kernels(dim_rep=8, concurrent=1, **w2v):
     bubbles in a 20-replicate run)."""
     import networkx as nx
     import torch
-    key = (torch.cuda.current_device(), int(dim_rep), concurrent > 1, tuple(sorted(w2v.items())))
+    key = (torch.cuda.current_device(), int(dim_rep), tuple(sorted(w2v.items())))
     if key in _PRELOADED:
         return
     g = nx.MultiGraph()
     g.add_edges_from([(i, (i + 1) % 12) for i in range(12)] + [(0, 6), (0, 6), (3, 3)])
     csr = GraphCSR.from_networkx(g).to_device()
-    dw = real_replicate(csr, 0, 0, dim_rep, niter=2, wait=False, concurrent=concurrent, **w2v)
+    dw = real_replicate(csr, 0, 0, dim_rep, niter=2, wait=False, **w2v)
     pg = torch.zeros(1, dtype=torch.int32, device='cuda')
     one = torch.empty(1, dtype=torch.float32, device='cuda')
     _lib.call('gw_cosine_pairs', int(dim_rep), _lib.ptr(dw._pending['syn0']), 1, _lib.ptr(pg),
               _lib.ptr(pg), _lib.ptr(one), _lib.stream_ptr())
     dw.finish_word2vec()
-    null = _NullJob(g, 0, 0, dim_rep, 10, 2, dict(concurrent=concurrent, **w2v)).finish()
+    null = _NullJob(g, 0, 0, dim_rep, 10, 2, dict(w2v)).finish()
     if null.numel() > 0:
         _lib.call('gw_sort_f32', _lib.ptr(null), null.numel(), _lib.stream_ptr())
     torch.cuda.synchronize()
@@ -250,9 +244,7 @@ def _run_rolling(n_units, nstreams, enqueue, finish, timeline=None):
     """Keeps up to ``nstreams`` units in flight, unit i on CUDA stream i % nstreams: before unit i is
     enqueued, unit i - nstreams (the previous one on that stream) is finished, so there is no
     barrier between rounds -- the other streams keep the GPU busy meanwhile -- and at most
-    ``nstreams`` walk corpora are alive.  ``enqueue(i, together)`` and ``finish(i, job)`` run with
-    the unit's stream current; ``together`` = number of units of the unit's round (the last round
-    may be smaller: its trainings take a larger share of the GPU's workers).  Units are finished in
+    ``nstreams`` replicates are alive.  ``enqueue(i)`` and ``finish(i, job)`` run with the unit's stream current.  Units are finished in
     order.  ``timeline`` (a list) receives ``(unit, stream, begin_ms, end_ms)`` of the device work
     enqueued by ``enqueue``, measured with CUDA events relative to the first unit's begin."""
     import torch
@@ -272,7 +264,7 @@ def _run_rolling(n_units, nstreams, enqueue, finish, timeline=None):
             if timeline is not None:
                 e0 = torch.cuda.Event(enable_timing=True)
                 e0.record()
-            inflight[k] = (i, enqueue(i, min(nstreams, n_units - (i - k))))
+            inflight[k] = (i, enqueue(i))
             if timeline is not None:
                 e1 = torch.cuda.Event(enable_timing=True)
                 e1.record()
@@ -294,7 +286,7 @@ def _run_rolling(n_units, nstreams, enqueue, finish, timeline=None):
 def run_walks_many(graph, n_replicates, base_seed=None, concurrent=DEFAULT_CONCURRENT,
                    walk_length=10, niter=100, vector_size=8, **w2v):
     """``[run_walks(graph, ...) for _ in range(n_replicates)]`` (cli.py:200-203) with up to
-    ``concurrent`` replicates trained at once on separate CUDA streams.  Returns the DeepWalk
+    ``concurrent`` replicates in flight on separate CUDA streams.  Returns the DeepWalk
     objects (``.model.wv`` set)."""
     _lib.require_cuda()
     if base_seed is None:
@@ -302,16 +294,15 @@ def run_walks_many(graph, n_replicates, base_seed=None, concurrent=DEFAULT_CONCU
     csr = GraphCSR.from_networkx(graph).to_device() if not isinstance(graph, GraphCSR) else graph.to_device()
     out = []
 
-    def enqueue(rep, together):
-        return real_replicate(csr, base_seed, rep, vector_size, walk_length, niter, wait=False,
-                              concurrent=together, **w2v)
+    def enqueue(rep):
+        return real_replicate(csr, base_seed, rep, vector_size, walk_length, niter, wait=False, **w2v)
 
     def finish(rep, dw):
         dw.finish_word2vec()
         out.append(dw)
-    nstreams = fit_concurrent(concurrent, csr.nnz, niter, walk_length)
+    nstreams = fit_concurrent(concurrent, csr.n, vector_size)
     if min(nstreams, n_replicates) > 1:
-        preload_kernels(vector_size, 2, **w2v)
+        preload_kernels(vector_size, **w2v)
     _run_rolling(n_replicates, nstreams, enqueue, finish)
     return out
 
@@ -325,16 +316,15 @@ def null_replicates_many(mg, n_replicates, base_seed=None, concurrent=DEFAULT_CO
         base_seed = random.getrandbits(64)
     out = []
 
-    def enqueue(rep, together):
-        return _NullJob(mg, base_seed, rep, vector_size, walk_length, niter,
-                        dict(concurrent=together, **w2v), degrees=degrees)
+    def enqueue(rep):
+        return _NullJob(mg, base_seed, rep, vector_size, walk_length, niter, dict(w2v), degrees=degrees)
 
     def finish(rep, job):
         out.append((job.dw, job.finish(keep_model=keep_model).cpu().numpy()))
     degrees = multigraph_degrees(mg)
-    nstreams = fit_concurrent(concurrent, int(degrees.sum()), niter, walk_length)
+    nstreams = fit_concurrent(concurrent, len(degrees), vector_size)
     if min(nstreams, n_replicates) > 1:
-        preload_kernels(vector_size, 2, **w2v)
+        preload_kernels(vector_size, **w2v)
     _run_rolling(n_replicates, nstreams, enqueue, finish)
     return out
 
@@ -369,11 +359,11 @@ def run_genewalk(mg, genes, nreps_graph=3, nreps_null=3, alpha_fdr=1, gene_id_ty
     d_pg = torch.from_numpy(np.ascontiguousarray(pairs['pair_gene'], dtype=np.int32)).cuda()
     d_po = torch.from_numpy(np.ascontiguousarray(pairs['pair_go'], dtype=np.int32)).cuda()
 
-    def enqueue(i, together):
+    def enqueue(i):
         kind, rep = units[i]
         if kind == KIND_REAL:
             logger.info('real replicate %d/%d on rank %d' % (rep + 1, nreps_graph, rank))
-            dw = real_replicate(csr, base_seed, rep, dim_rep, wait=False, concurrent=together, **w2v)
+            dw = real_replicate(csr, base_seed, rep, dim_rep, wait=False, **w2v)
             # gene-GO similarities straight from the device table (rows are graph node ids, the
             # index space of `pairs`; every node of a pair has an edge, hence walks, hence a row):
             # perform_statistics.py:102 without the round trip through host vectors
@@ -384,8 +374,7 @@ def run_genewalk(mg, genes, nreps_graph=3, nreps_null=3, alpha_fdr=1, gene_id_ty
             local_sims[rep] = sims
             return dw
         logger.info('null replicate %d/%d on rank %d' % (rep + 1, nreps_null, rank))
-        return _NullJob(mg, base_seed, rep, dim_rep, 10, 100, dict(concurrent=together, **w2v),
-                        degrees=degrees)
+        return _NullJob(mg, base_seed, rep, dim_rep, 10, 100, dict(w2v), degrees=degrees)
 
     def finish(i, job):
         kind, rep = units[i]
@@ -394,14 +383,12 @@ def run_genewalk(mg, genes, nreps_graph=3, nreps_null=3, alpha_fdr=1, gene_id_ty
                 job.finish_word2vec()
                 nvs[rep] = job.model.wv
             job._pending = None
-            job.walks = []            # release the token array
         else:
             local_null[rep] = job.finish()
-            job.dw.walks = []
     timeline = [] if return_parts else None
-    nstreams = fit_concurrent(concurrent, csr.nnz)
+    nstreams = fit_concurrent(concurrent, csr.n, dim_rep)
     if min(nstreams, len(units)) > 1:
-        preload_kernels(dim_rep, 2, **w2v)
+        preload_kernels(dim_rep, **w2v)
     _run_rolling(len(units), nstreams, enqueue, finish, timeline)
     torch.cuda.synchronize()
     t_units = time.perf_counter()

@@ -1,4 +1,5 @@
-"""Deterministic synthetic GeneWalk networks; shared by tests and bench.py."""
+"""Deterministic synthetic GeneWalk networks: the workloads of bench.py, of the
+parity studies and of the tests."""
 import numpy as np
 import networkx as nx
 

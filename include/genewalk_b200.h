@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GW_VERSION 100
+#define GW_VERSION 200
 
 typedef void *gw_stream_t; /* cudaStream_t */
 
@@ -87,6 +87,11 @@ int gw_walk_uniform(int32_t n, int64_t nnz, const int32_t *row_ptr, const int32_
                     int32_t niter, int32_t L, uint64_t seed, uint64_t stride, int64_t slot_begin,
                     int64_t slot_end, int32_t *tokens, gw_stream_t stream);
 
+/* counts[v] = number of occurrences of v in the W = niter*nnz walks gw_walk_uniform(seed) draws,
+ * without storing them (gensim build_vocab's raw counts; the trainer regenerates the walks). */
+int gw_walk_count(int32_t n, int64_t nnz, const int32_t *row_ptr, const int32_t *col_idx,
+                  int32_t niter, int32_t L, uint64_t seed, int64_t *counts, gw_stream_t stream);
+
 /* ---- (3) skip-gram negative sampling ------------------------------------------------------
  * Replaces gensim.models.Word2Vec(sentences=walks, sg=1, vector_size=d, window=1, min_count=1,
  * negative=K, sample=0) as called at deepwalk.py:135-139. */
@@ -113,54 +118,74 @@ int gw_alias_build(int32_t n, const int64_t *counts, double power, gw_alias_entr
 int gw_sgns_init(int32_t n, int32_t d, const int32_t *rank_of_node, const float *rng_rows,
                  float *syn0, float *syn1neg, gw_stream_t stream);
 
-/* Trains epochs [epoch_begin, epoch_end) of `epochs` over the W stored walks (window 1), stored in
+/* One work unit of the trainer's queue: `count` consecutive walks starting at walk id `first`;
+ * `node` = start node of walk `first` (owner of adjacency entry first / niter; -1 when the plan was
+ * made without a graph).  16 bytes, 16-byte aligned. */
+typedef struct {
+    int64_t first;
+    int32_t count;
+    int32_t node;
+} gw_sgns_unit;
+
+/* How the corpus is cut into units (gw_sgns_plan):
+ *   GW_PLAN_CHUNK  units of unit_walks consecutive walks (the last one shorter), like gensim's
+ *                  jobs; a unit may span several start nodes;
+ *   GW_PLAN_BURST  a unit never crosses a start node: the niter*len(graph[v]) walks that start at v
+ *                  (deepwalk.py:67-70,197) are one unit, cut into ceil(len/unit_walks) near-equal
+ *                  pieces when longer than unit_walks. */
+enum gw_plan_policy { GW_PLAN_CHUNK = 0, GW_PLAN_BURST = 1 };
+
+/* number of gw_sgns_unit entries gw_sgns_plan may write (host-side arithmetic) */
+int64_t gw_sgns_plan_capacity(int32_t n, int64_t W, int64_t unit_walks, int32_t policy);
+
+/* Writes the units of a W = niter*A walk corpus in corpus order and *num_units (device int64).
+ * row_ptr may be NULL for GW_PLAN_CHUNK (corpora that do not come from gw_walk_uniform). */
+int gw_sgns_plan(int32_t n, const int32_t *row_ptr, int32_t niter, int64_t W, int64_t unit_walks,
+                 int32_t policy, gw_sgns_unit *units, int64_t capacity, int64_t *num_units,
+                 gw_stream_t stream);
+
+/* Trains epochs [epoch_begin, epoch_end) of `epochs` over the W walks of the corpus (window 1), in
  * the corpus order the learning-rate schedule refers to (for GeneWalk: the reference's node-major
- * order, gw_walk_uniform with stride 0).
+ * order, walk id w = e*niter + it).
+ * The walks are either read from `tokens` (position-major [L][W], slot p = walk p; a negative token
+ * ends its walk early: ragged corpora are padded with -1) or, with tokens == NULL, regenerated by
+ * the workers from (row_ptr, col_idx, niter, walk_seed) exactly as gw_walk_uniform draws them, so
+ * that the corpus never has to exist in memory (C2: 6 GB per replicate).
  * Parallel structure = gensim's: the corpus is cut into jobs of job_walks consecutive walks
  * (gensim batch_words=10000 -> 1000 walks of 10); every walk of job j of epoch ep is trained with
  * alpha = max(alpha_min, alpha0 - (alpha0-alpha_min) * ((ep + j*job_walks/W) / epochs))
  * (gensim _get_next_alpha).  `lanes` workers (a worker = one group of d/2 <= 32 GPU threads; the
- * analogue of gensim's `workers`) take chunks of chunk_walks consecutive walks (chunk_walks divides
- * job_walks) from a queue and train them concurrently, racing on the tables with red.global.add
- * (Hogwild).  The queue deals chunks in corpus order from `streams` equal slices of the corpus in
- * turn (streams = 1: plain corpus order), which bounds the number of workers that train walks
- * starting at the same node at ~lanes/streams.  lanes = 1 is the sequential statement of the
- * algorithm (bit-exact against the oracle); lanes / chunk_walks / streams = 0 pick
- * gw_sgns_auto_shape().
+ * analogue of gensim's `workers`) take the units of `units` (gw_sgns_plan) from a queue in order
+ * and train each unit's walks one after the other, racing on the tables with red.global.add
+ * (Hogwild).  lanes = 1 is the sequential statement of the algorithm (bit-exact against the
+ * oracle for any plan).
  * Pair q = 2i + (j>i) of walk w draws its K negatives from Philox4x32-10(ctr {lo32(w), hi32(w),
  * (q<<4)|c, (ep<<8)|0x53}, key = seed): negative t uses words 2(t-1), 2(t-1)+1:
  * slot = mulhi32(x0, n), target = (x1>>16) < min(65535, floor(prob[slot]*2^16)) ? slot : alias[slot];
  * a draw equal to the centre is skipped.  Update rule = gensim w2v_fast_sentence_sg_neg, all
  * arithmetic unfused fp32; the dot product sums d/2 (<= 32) chunks left to right and combines the
  * chunk sums by a pairwise tree.  d in {8,16,32,64,128}; K <= 32; L <= 4096.
- * A negative token ends its walk early (ragged corpora are padded with -1).
  * flags (gw_sgns_flags):
- *   GW_SGNS_SHARED_SM  the kernel keeps the noise table in global memory (L1/L2) instead of copying
- *     it into ~150 KB of shared memory per CTA, so that kernels of other replicates, launched on
- *     other streams, can run on the same SMs (independent replicates have independent tables:
- *     training several at once relieves the same-row reduction contention in L2).
- *   GW_SGNS_PER_PAIR / GW_SGNS_MERGED  how a worker's updates of the rows it visits twice reach
- *     memory.  PER_PAIR: one reduction per (pair, row) in gensim's order.  MERGED: the two updates
- *     of syn1neg[centre] inside a step, and the two updates of syn0[walk[j]] from steps j-1 and
- *     j+1, are summed in registers and reduced once; rows are still read from the table right
- *     before use and the worker adds its own held-back update, so its arithmetic sees every one of
- *     its updates.  Default (neither flag): MERGED when 1 < lanes <= n/12 -- many rows per worker,
- *     where the interleaving with other workers' updates is arbitrary anyway and holding an update
- *     back for two steps is measured to be neutral -- else PER_PAIR.  Both orders are bit-exact
- *     against the oracle when run with lanes == 1. */
-enum gw_sgns_flags { GW_SGNS_SHARED_SM = 1, GW_SGNS_PER_PAIR = 2, GW_SGNS_MERGED = 4 };
-int gw_sgns_train(int32_t n, int32_t d, const int32_t *tokens, int64_t W, int32_t L,
+ *   GW_SGNS_MERGED  how a worker's updates of the rows it visits twice reach memory.  Default:
+ *     one reduction per (pair, row) in gensim's order.  MERGED: the two updates of syn1neg[centre]
+ *     inside a step, and the two updates of syn0[walk[j]] from steps j-1 and j+1, are summed in
+ *     registers and reduced once; rows are still read from the table right before use and the
+ *     worker adds its own held-back update, so its arithmetic sees every one of its updates.
+ *     Both orders are bit-exact against the oracle when run with lanes == 1. */
+enum gw_sgns_flags { GW_SGNS_MERGED = 4 };
+int gw_sgns_train(int32_t n, int32_t d, const int32_t *tokens, const int32_t *row_ptr,
+                  const int32_t *col_idx, int32_t niter, uint64_t walk_seed, int64_t W, int32_t L,
                   int32_t window, int32_t K, int32_t epochs, int32_t epoch_begin,
                   int32_t epoch_end, double alpha0, double alpha_min, int64_t job_walks,
-                  int64_t chunk_walks, int64_t streams, const gw_alias_entry *alias_table,
-                  float *syn0, float *syn1neg, uint64_t seed, int64_t lanes, int32_t flags,
-                  gw_stream_t stream);
+                  const gw_sgns_unit *units, const int64_t *num_units,
+                  const gw_alias_entry *alias_table, float *syn0, float *syn1neg, uint64_t seed,
+                  int64_t lanes, int32_t flags, gw_stream_t stream);
 
-/* the (lanes, chunk_walks, streams) gw_sgns_train uses when they are passed as 0 (host pointers).
- * concurrent = number of trainings the caller runs at once on this GPU (separate streams, flag
- * GW_SGNS_SHARED_SM): they share the GPU's resident workers; gw_sgns_train itself assumes 1. */
-int gw_sgns_auto_shape(int32_t n, int64_t W, int64_t job_walks, int32_t concurrent,
-                       int64_t *lanes_out, int64_t *chunk_out, int64_t *streams_out);
+/* The default (lanes, unit_walks, policy) of a training (host pointers).  A function of the
+ * network alone: it does not depend on how many trainings share the GPU, nor on how many GPUs the
+ * replicates are spread over, so a seed gives the same statistics at every GPU count. */
+int gw_sgns_auto_shape(int32_t n, int64_t W, int64_t job_walks, int64_t *lanes_out,
+                       int64_t *unit_walks_out, int32_t *policy_out);
 
 /* ---- (4) similarity statistics ------------------------------------------------------------ */
 

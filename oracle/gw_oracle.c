@@ -220,11 +220,20 @@ static int32_t draw_target(int sampler, draw_state *ds, int32_t V, int t)
 /* sigmoid through gensim's EXP_TABLE; returns 0 when f is saturated (the target is skipped).
  * For the largest floats below 6, f + 6 rounds up to 12.0f and gensim's index becomes 1000, one past
  * its table (it then reads the adjacent static array); clamped to the last entry. */
+
+/* EXP_TABLE index scale: gensim writes (f + MAX_EXP) * (EXP_TABLE_SIZE / MAX_EXP / 2) with Cython DEF
+ * constants 1000 and 6.  Whether the compiled extension folds that to 83.333... (true division) or
+ * to 83 (C-style integer division, as in the original word2vec.c) depends on how the .pyx was
+ * cythonized; it cannot be read off the published source.  Default: true division.  The pin script
+ * (tools/pin_gensim.py) runs real gensim against both and reports which one it is. */
+static double g_exp_scale = (double)GWO_EXP_TABLE_SIZE / (double)GWO_MAX_EXP / 2.0;
+void gwo_set_exp_scale(double scale) { g_exp_scale = scale; }
+double gwo_get_exp_scale(void) { return g_exp_scale; }
+
 static int table_sigmoid(float f, const float *exp_table, float *sig)
 {
     if (f <= -(float)GWO_MAX_EXP || f >= (float)GWO_MAX_EXP) return 0;
-    int ei = (int)((double)(f + (float)GWO_MAX_EXP) *
-                   ((double)GWO_EXP_TABLE_SIZE / (double)GWO_MAX_EXP / 2.0));
+    int ei = (int)((double)(f + (float)GWO_MAX_EXP) * g_exp_scale);
     if (ei >= GWO_EXP_TABLE_SIZE) ei = GWO_EXP_TABLE_SIZE - 1;
     *sig = exp_table[ei];
     return 1;

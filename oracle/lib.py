@@ -85,6 +85,15 @@ def walk_uniform(row_ptr, col_idx, niter, L, seed, stride=1, slot_begin=0, slot_
     return out
 
 
+def set_exp_scale(scale):
+    """EXP_TABLE index scale of the oracle's sigmoid (default 1000/6/2; the alternative 83.0 is what
+    C-style folding of gensim's DEF constants would give): see tools/pin_gensim.py."""
+    L = lib()
+    L.gwo_set_exp_scale.argtypes = [ctypes.c_double]
+    L.gwo_set_exp_scale.restype = None
+    L.gwo_set_exp_scale(float(scale))
+
+
 def exp_table():
     t = np.empty(1000, dtype=np.float32)
     lib().gwo_exp_table(_p(t, c_f32p))

@@ -75,6 +75,55 @@ def fdrcorrection(pvals, alpha=0.05, method='indep', is_sorted=False):
     return q <= alpha, q
 
 
+class ShimGOTerm(object):
+    def __init__(self, id, name, namespace):
+        self.id, self.name, self.namespace = id, name, namespace
+
+
+class ShimGODag(dict):
+    """goatools.obo_parser.GODag stand-in (goatools is absent here): id -> term with .id, .name,
+    .namespace for the non-obsolete [Term] stanzas of an OBO file, alt_ids included -- the part of
+    GODag that nx_mg_assembler.py:414-422 reads."""
+
+    def __init__(self, obo_file, *args, **kwargs):
+        super().__init__()
+        block = None
+        with open(obo_file) as f:
+            for line in list(f) + ['[End]']:
+                line = line.strip()
+                if line.startswith('['):
+                    if block and 'id' in block and not block.get('is_obsolete'):
+                        term = ShimGOTerm(block['id'], block.get('name'), block.get('namespace'))
+                        for key in [block['id']] + block.get('alt_id', []):
+                            self.setdefault(key, term)
+                    block = {} if line == '[Term]' else None
+                elif block is not None and ': ' in line:
+                    k, v = line.split(': ', 1)
+                    if k == 'alt_id':
+                        block.setdefault('alt_id', []).append(v)
+                    elif k == 'is_obsolete':
+                        block[k] = v.startswith('true')
+                    else:
+                        block.setdefault(k, v)
+
+
+def import_assembler():
+    """The reference's nx_mg_assembler module (UserNxMgAssembler) with goatools stubbed."""
+    if not available():
+        raise RuntimeError('/root/reference is not present (GPU box): golden fixtures are used')
+    if 'goatools' not in sys.modules:
+        g = types.ModuleType('goatools')
+        go = types.ModuleType('goatools.obo_parser')
+        go.GODag = ShimGODag
+        g.obo_parser = go
+        sys.modules['goatools'] = g
+        sys.modules['goatools.obo_parser'] = go
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    import importlib
+    return importlib.import_module('genewalk.nx_mg_assembler')
+
+
 def available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, 'genewalk'))
 

@@ -9,7 +9,7 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from genewalk_b200.replicates import run_genewalk, plan_units   # noqa: E402
-from tests import graphs                                         # noqa: E402
+from genewalk_b200 import workloads as graphs                                         # noqa: E402
 
 
 def main():

@@ -34,7 +34,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
 from oracle import ref_shim          # noqa: E402
-from tests import graphs             # noqa: E402
+from genewalk_b200 import workloads as graphs             # noqa: E402
 
 warnings.filterwarnings('ignore')
 

@@ -13,7 +13,7 @@ HEADER = os.path.join(ROOT, 'include', 'genewalk_b200.h')
 def declared_functions():
     src = open(HEADER).read()
     src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
-    decl = re.findall(r'\b(?:int|long long|const char \*)\s*(gw_\w+)\s*\(([^;]*?)\)\s*;', src, flags=re.S)
+    decl = re.findall(r'\b(?:int|int64_t|long long|const char \*)\s*(gw_\w+)\s*\(([^;]*?)\)\s*;', src, flags=re.S)
     return {name: [a.strip() for a in args.split(',')] if args.strip() != 'void' else []
             for name, args in decl}
 
@@ -23,7 +23,8 @@ def test_header_declares_the_hot_path():
     for name in ('gw_walk_uniform', 'gw_sgns_train', 'gw_alias_build', 'gw_config_model',
                  'gw_csr_from_edges', 'gw_cosine_pairs', 'gw_null_similarities', 'gw_sort_f32',
                  'gw_psim', 'gw_bh_segmented', 'gw_log_stats', 'gw_count_tokens', 'gw_vocab_rank',
-                 'gw_sgns_init', 'gw_mean_sem_f32'):
+                 'gw_sgns_init', 'gw_mean_sem_f32', 'gw_walk_count', 'gw_sgns_plan',
+                 'gw_sgns_plan_capacity', 'gw_sgns_auto_shape'):
         assert name in fns
     # every entry point cites the reference call site it replaces
     text = open(HEADER).read()
@@ -40,7 +41,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     fns = declared_functions()
     for name, args in fns.items():
         assert hasattr(lib, name), 'missing export %s' % name
-    assert lib.gw_version() == 100
+    assert lib.gw_version() == _lib.ABI_VERSION == 200
     assert isinstance(_lib.last_error(), str)
     assert _lib.launch_count() >= 0
 
@@ -52,7 +53,9 @@ def test_ctypes_table_matches_header_arity():
         assert name in fns, '%s bound but not declared in the header' % name
         assert len(argtypes) == len(fns[name]), '%s: %d ctypes args vs %d declared' % (
             name, len(argtypes), len(fns[name]))
-    bound = set(_lib.SIGNATURES) | {'gw_last_error', 'gw_launch_count'}
+    for name, argtypes in _lib.INT64_RETURNS.items():
+        assert len(argtypes) == len(fns[name])
+    bound = set(_lib.SIGNATURES) | set(_lib.INT64_RETURNS) | {'gw_last_error', 'gw_launch_count'}
     assert set(fns) == bound
 
 

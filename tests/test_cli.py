@@ -8,7 +8,7 @@ import pandas as pd
 import pytest
 
 from genewalk_b200 import cli
-from tests import graphs
+from genewalk_b200 import workloads as graphs
 
 
 def _args(tmp, **kw):

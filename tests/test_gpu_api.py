@@ -22,7 +22,7 @@ from genewalk_b200.keyedvectors import NodeVectors  # noqa: E402
 from genewalk_b200.csr import GraphCSR, multigraph_degrees  # noqa: E402
 from oracle import lib as olib  # noqa: E402
 from oracle import stats_ref  # noqa: E402
-from tests import graphs  # noqa: E402
+from genewalk_b200 import workloads as graphs  # noqa: E402
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
@@ -368,7 +368,7 @@ def test_word2vec_enqueue_then_finish():
     a.word2vec(lanes=1, sgns_seed=9)
     b = DeepWalk(mg, 10, 20, seed=5)
     b.get_walks()
-    assert b.word2vec(lanes=1, sgns_seed=9, wait=False, shared_sm=True) is None
+    assert b.word2vec(lanes=1, sgns_seed=9, wait=False) is None
     assert b.model is None
     b.finish_word2vec()
     assert b.model.wv.index_to_key == a.model.wv.index_to_key
@@ -392,7 +392,8 @@ def test_run_walks_many_equals_serial_replicates():
 
 def test_run_genewalk_concurrency_does_not_change_inputs_or_statistics():
     """run_genewalk(concurrent=3) vs concurrent=1 at lanes=1: identical similarities, null
-    distribution and table."""
+    distribution and table; and the number of replicates in flight never changes the shape of a
+    training (same workers, same plan: results do not depend on GPU fill or GPU count)."""
     from genewalk_b200.replicates import run_genewalk
     mg, genes = graphs.modular_gene_go_network(120, 30, 4, 500, 300, 40, seed=13)
     kw = dict(nreps_graph=2, nreps_null=3, alpha_fdr=1, gene_id_type='custom', base_seed=3,
@@ -402,3 +403,10 @@ def test_run_genewalk_concurrency_does_not_change_inputs_or_statistics():
     assert np.array_equal(p1['sims'].cpu().numpy(), p3['sims'].cpu().numpy())
     assert np.array_equal(p1['null'], p3['null'])
     assert d1.equals(d3)
+    from genewalk_b200.replicates import run_walks_many
+    shapes = []
+    for conc in (1, 4):
+        dws = run_walks_many(mg, 4, base_seed=2, concurrent=conc, niter=20)
+        shapes.append({(dw.train_shape['lanes'], dw.train_shape['unit_walks'], dw.train_shape['policy'])
+                       for dw in dws})
+    assert shapes[0] == shapes[1] and len(shapes[0]) == 1

@@ -12,7 +12,7 @@ torch = pytest.importorskip('torch')
 from genewalk_b200 import _lib                      # noqa: E402
 from genewalk_b200.csr import GraphCSR              # noqa: E402
 from genewalk_b200.deepwalk import DeepWalk         # noqa: E402
-from tests import graphs                            # noqa: E402
+from genewalk_b200 import workloads as graphs                            # noqa: E402
 
 
 @pytest.fixture(scope='module')

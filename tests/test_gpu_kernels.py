@@ -12,7 +12,7 @@ torch = pytest.importorskip('torch')
 from genewalk_b200 import _lib  # noqa: E402
 from oracle import lib as olib  # noqa: E402
 from oracle import config_model_ref, stats_ref  # noqa: E402
-from tests import graphs  # noqa: E402
+from genewalk_b200 import workloads as graphs  # noqa: E402
 
 
 _KEEP = []   # device tensors whose raw pointers were handed to the library stay alive per test
@@ -246,16 +246,45 @@ def sgns_case(n, m, niter, L, d, K, epochs, seed):
     return tok, prob, alias, syn0, syn1
 
 
+def gpu_plan(n, W, unit_walks, policy, row_ptr=None, niter=1):
+    """gw_sgns_plan -> (device units tensor, device num_units, host copy of the units)."""
+    lib = _lib.load()
+    cap = int(lib.gw_sgns_plan_capacity(n, W, unit_walks, policy))
+    units = torch.empty((cap, 2), dtype=torch.int64, device='cuda')
+    num = torch.zeros(1, dtype=torch.int64, device='cuda')
+    d_rp = dev(row_ptr, np.int32) if row_ptr is not None else None
+    _lib.call('gw_sgns_plan', n, _lib.ptr(d_rp), niter, W, unit_walks, policy, _lib.ptr(units), cap,
+              _lib.ptr(num), st())
+    torch.cuda.synchronize()
+    k = int(num.item())
+    raw = units[:k].cpu().numpy()
+    host = np.zeros(k, dtype=[('first', np.int64), ('count', np.int32), ('node', np.int32)])
+    host['first'] = raw[:, 0]
+    host['count'] = (raw[:, 1] & 0xffffffff).astype(np.int64).astype(np.int32)
+    host['node'] = (raw[:, 1] >> 32).astype(np.int32)
+    return units, num, host
+
+
 def gpu_sgns(tok, n, d, K, epochs, prob, alias, syn0, syn1, seed, lanes, job_walks=1000,
-             alpha0=0.025, alpha_min=0.0001, chunk_walks=0, streams=0, shared_sm=0, flags=0):
+             alpha0=0.025, alpha_min=0.0001, unit_walks=0, policy=0, flags=0, graph=None):
+    """graph = (row_ptr, col_idx, niter, walk_seed): the trainer regenerates the walks (tok is then
+    only used for its shape); otherwise it reads the token array."""
     L, W = tok.shape
     table = np.empty((n, 2), dtype=np.int32)
     table[:, 0] = prob.view(np.int32)
     table[:, 1] = alias
     d0, d1 = dev(syn0), dev(syn1)
-    _lib.call('gw_sgns_train', n, d, _lib.ptr(dev(tok, np.int32)), W, L, 1, K, epochs, 0, epochs,
-              alpha0, alpha_min, job_walks, chunk_walks, streams, _lib.ptr(dev(table)), _lib.ptr(d0), _lib.ptr(d1),
-              seed, lanes, shared_sm | flags, st())
+    if unit_walks == 0:
+        unit_walks = job_walks if lanes == 1 else 8
+    row_ptr = graph[0] if graph is not None else None
+    units, num, _ = gpu_plan(n, W, unit_walks, policy, row_ptr, graph[2] if graph is not None else 1)
+    if graph is None:
+        args = (_lib.ptr(dev(tok, np.int32)), None, None, 0, 0)
+    else:
+        args = (None, _lib.ptr(dev(graph[0], np.int32)), _lib.ptr(dev(graph[1], np.int32)), graph[2], graph[3])
+    _lib.call('gw_sgns_train', n, d, *args, W, L, 1, K, epochs, 0, epochs, alpha0, alpha_min, job_walks,
+              _lib.ptr(units), _lib.ptr(num), _lib.ptr(dev(table)), _lib.ptr(d0), _lib.ptr(d1),
+              seed, lanes, flags, st())
     torch.cuda.synchronize()
     return d0.cpu().numpy(), d1.cpu().numpy()
 
@@ -274,11 +303,81 @@ def test_sgns_sequential_bit_exact(n, m, niter, L, d, K, epochs):
     want0, want1 = syn0.copy(), syn1.copy()
     olib.sgns_train(tok, n, d, want0, want1, sampler=1, K=K, epochs=epochs, job_walks=100,
                     alias_prob=prob, alias_idx=alias, seed=seed)
-    for shared_sm in (0, 1):     # noise table in shared memory / in global memory: same bits
+    # sequential = one worker: the plan (how the corpus is cut into units) cannot matter
+    for unit_walks, policy in ((100, 0), (7, 0), (1000, 0)):
         got0, got1 = gpu_sgns(tok, n, d, K, epochs, prob, alias, syn0, syn1, seed, lanes=1,
-                              job_walks=100, shared_sm=shared_sm)
+                              job_walks=100, unit_walks=unit_walks, policy=policy)
         assert np.array_equal(got0.view(np.uint32), want0.view(np.uint32))
         assert np.array_equal(got1.view(np.uint32), want1.view(np.uint32))
+
+
+@pytest.mark.parametrize('n,m,niter,L,d,K,epochs', [(40, 120, 3, 10, 8, 5, 3),
+                                                    (40, 120, 2, 10, 16, 5, 2),
+                                                    (30, 90, 5, 7, 8, 3, 2),
+                                                    (25, 60, 3, 6, 64, 5, 1),
+                                                    (25, 60, 3, 13, 128, 5, 1),
+                                                    (12, 14, 6, 10, 8, 5, 3)])
+def test_sgns_regenerated_walks_bit_exact(n, m, niter, L, d, K, epochs):
+    """tokens == NULL: the workers regenerate every walk from its Philox counter (no corpus in
+    memory).  Sequential run, both plan policies, per-pair and merged order: the same bits as the
+    oracle trained on the oracle's walks."""
+    wseed = 1000 + d
+    row_ptr, col_idx = graphs.csr_arrays(n, m, seed=7 + d, self_loops=2)
+    tok = olib.walk_uniform(row_ptr, col_idx, niter, L, wseed, 0)
+    counts = np.bincount(tok.ravel(), minlength=n)
+    prob, alias = olib.alias_table(counts)
+    syn0, syn1 = olib.gensim_init_weights(n, d, seed=1)
+    for merged in (False, True):
+        want0, want1 = syn0.copy(), syn1.copy()
+        olib.sgns_train(tok, n, d, want0, want1, sampler=1, K=K, epochs=epochs, job_walks=50,
+                        alias_prob=prob, alias_idx=alias, seed=5, merged=merged)
+        for unit_walks, policy in ((50, 0), (7, 0), (1000, 1), (13, 1)):
+            got0, got1 = gpu_sgns(tok, n, d, K, epochs, prob, alias, syn0, syn1, 5, lanes=1, job_walks=50,
+                                  unit_walks=unit_walks, policy=policy, flags=4 if merged else 0,
+                                  graph=(row_ptr, col_idx, niter, wseed))
+            assert np.array_equal(got0.view(np.uint32), want0.view(np.uint32)), (merged, unit_walks, policy)
+            assert np.array_equal(got1.view(np.uint32), want1.view(np.uint32))
+
+
+def test_walk_count_equals_token_histogram():
+    """gw_walk_count (vocabulary without a stored corpus) == bincount of the oracle's walks, on the
+    shared-memory path (n <= 49152) and the global-atomics path."""
+    for n, m, niter in ((300, 2000, 7), (60000, 90000, 2)):
+        row_ptr, col_idx = graphs.csr_arrays(n, m, seed=3, self_loops=3)
+        tok = olib.walk_uniform(row_ptr, col_idx, niter, 10, 99, 0)
+        counts = torch.empty(n, dtype=torch.int64, device='cuda')
+        _lib.call('gw_walk_count', n, len(col_idx), _lib.ptr(dev(row_ptr, np.int32)),
+                  _lib.ptr(dev(col_idx, np.int32)), niter, 10, 99, _lib.ptr(counts), st())
+        torch.cuda.synchronize()
+        assert np.array_equal(counts.cpu().numpy(), np.bincount(tok.ravel(), minlength=n))
+
+
+def test_sgns_plan_units():
+    """gw_sgns_plan: the units tile the corpus exactly, in order; chunk units have the asked size;
+    burst units never cross a start node, carry it, and are near-equal pieces of long bursts."""
+    n, niter = 500, 10
+    row_ptr, col_idx = graphs.csr_arrays(n, 4000, seed=5, self_loops=2)
+    W = niter * len(col_idx)
+    start_of_walk = np.repeat(np.repeat(np.arange(n), np.diff(row_ptr)), niter)
+    for policy, unit_walks in ((0, 64), (0, 1000), (1, 100), (1, 25), (1, 100000)):
+        _, _, u = gpu_plan(n, W, unit_walks, policy, row_ptr, niter)
+        assert u['first'][0] == 0 and (u['count'] > 0).all() and (u['count'] <= unit_walks).all()
+        assert np.array_equal(u['first'][1:], (u['first'] + u['count'])[:-1])
+        assert u['first'][-1] + u['count'][-1] == W
+        assert np.array_equal(u['node'], start_of_walk[u['first']])
+        if policy == 0:
+            assert (u['count'][:-1] == unit_walks).all()
+        else:
+            assert np.array_equal(start_of_walk[u['first']], start_of_walk[u['first'] + u['count'] - 1])
+            burst = np.diff(row_ptr) * niter
+            pieces = np.bincount(u['node'], minlength=n)
+            assert np.array_equal(pieces, -(-burst // unit_walks))
+            big = np.argmax(burst)
+            c = u['count'][u['node'] == big]
+            assert c.max() - c.min() <= 1
+    # a plan without a graph (corpora given as lists of walks)
+    _, _, u = gpu_plan(10, 1234, 100, 0, None, 1)
+    assert len(u) == 13 and (u['node'] == -1).all() and u['count'][-1] == 34
 
 
 @pytest.mark.parametrize('n,m,niter,L,d,K,epochs', [(40, 120, 3, 10, 8, 5, 5),
@@ -288,7 +387,7 @@ def test_sgns_sequential_bit_exact(n, m, niter, L, d, K, epochs):
                                                     (30, 90, 2, 7, 32, 5, 2),
                                                     (12, 14, 6, 10, 8, 5, 3)])
 def test_sgns_merged_reductions_bit_exact(n, m, niter, L, d, K, epochs):
-    """GW_SGNS_MERGED (the Hogwild default) run sequentially: a worker sums its two updates of a row
+    """GW_SGNS_MERGED run sequentially: a worker sums its two updates of a row
     in registers and reduces once, computing on its own up-to-date view meanwhile.  Bit-exact against
     the oracle's restatement of that order (gw_oracle.c:walk_merged), which differs from gensim's
     per-pair order by float summation order only (amplified by the 1000-bin sigmoid table: the two
@@ -304,19 +403,19 @@ def test_sgns_merged_reductions_bit_exact(n, m, niter, L, d, K, epochs):
     olib.sgns_train(tok, n, d, pp0, pp1, sampler=1, K=K, epochs=epochs, job_walks=100,
                     alias_prob=prob, alias_idx=alias, seed=77)
     assert not np.array_equal(pp0, want0) and np.abs(pp0 - want0).max() < 0.05
-    for shared_sm in (0, 1):
-        got0, got1 = gpu_sgns(tok, n, d, K, epochs, prob, alias, syn0, syn1, 77, lanes=1,
-                              job_walks=100, shared_sm=shared_sm, flags=4)
-        assert np.array_equal(got0.view(np.uint32), want0.view(np.uint32))
-        assert np.array_equal(got1.view(np.uint32), want1.view(np.uint32))
-    # and PER_PAIR can be forced in Hogwild mode (finite; not bit-comparable)
-    hw0, _ = gpu_sgns(tok, n, d, K, epochs, prob, alias, syn0, syn1, 77, lanes=8, job_walks=100,
-                      chunk_walks=4, streams=1, flags=2)
-    assert np.isfinite(hw0).all()
+    got0, got1 = gpu_sgns(tok, n, d, K, epochs, prob, alias, syn0, syn1, 77, lanes=1,
+                          job_walks=100, flags=4)
+    assert np.array_equal(got0.view(np.uint32), want0.view(np.uint32))
+    assert np.array_equal(got1.view(np.uint32), want1.view(np.uint32))
+    # Hogwild mode in both orders (finite; not bit-comparable)
+    for flags in (0, 4):
+        hw0, _ = gpu_sgns(tok, n, d, K, epochs, prob, alias, syn0, syn1, 77, lanes=8, job_walks=100,
+                          unit_walks=4, flags=flags)
+        assert np.isfinite(hw0).all()
 
 
 def test_sgns_large_vocabulary_bit_exact():
-    """n > 56000: the noise table stays in global memory (no shared-memory copy); same bits."""
+    """A vocabulary larger than any shared-memory table (n = 70000): same bits."""
     n, d, K = 70000, 8, 5
     row_ptr, col_idx = graphs.csr_arrays(n, 120000, seed=9, power_law=False)
     tok = olib.walk_uniform(row_ptr, col_idx, 1, 10, 4, 0, 0, 3000)
@@ -329,7 +428,7 @@ def test_sgns_large_vocabulary_bit_exact():
     got0, got1 = gpu_sgns(tok, n, d, K, 2, prob, alias, syn0, syn1, 8, lanes=1)
     assert np.array_equal(got0, want0) and np.array_equal(got1, want1)
     # and the concurrent run on the same input stays finite and close in distribution
-    got0c, _ = gpu_sgns(tok, n, d, K, 2, prob, alias, syn0, syn1, 8, lanes=64, chunk_walks=8, streams=1)
+    got0c, _ = gpu_sgns(tok, n, d, K, 2, prob, alias, syn0, syn1, 8, lanes=64, unit_walks=8)
     assert np.isfinite(got0c).all()
     touched = counts > 0
     assert np.abs(got0c[touched] - want0[touched]).mean() < 0.02
@@ -358,7 +457,7 @@ def test_sgns_unsupported_raises():
 
 
 def test_sgns_hogwild_close_to_sequential():
-    """Concurrent workers (16 workers, 25-walk chunks on a 200-node graph) vs the sequential oracle on
+    """Concurrent workers (16 workers, 25-walk units on a 200-node graph) vs the sequential oracle on
     the same corpus and negatives: the runs differ only by stale reads and the order of float adds;
     the neighbour-similarity distributions agree."""
     from scipy.stats import ks_2samp
@@ -367,8 +466,7 @@ def test_sgns_hogwild_close_to_sequential():
     want0, want1 = syn0.copy(), syn1.copy()
     olib.sgns_train(tok, n, d, want0, want1, sampler=1, K=K, epochs=epochs, alias_prob=prob,
                     alias_idx=alias, seed=77)
-    got0, _ = gpu_sgns(tok, n, d, K, epochs, prob, alias, syn0, syn1, 77, lanes=16, chunk_walks=25,
-                       streams=2)
+    got0, _ = gpu_sgns(tok, n, d, K, epochs, prob, alias, syn0, syn1, 77, lanes=16, unit_walks=25)
     assert np.isfinite(got0).all()
     row_ptr, col_idx = graphs.csr_arrays(n, 1500, seed=21, self_loops=2)
     s_want = stats_ref.null_similarities(row_ptr, col_idx, want0)
@@ -377,23 +475,17 @@ def test_sgns_hogwild_close_to_sequential():
     assert abs(s_want.mean() - s_got.mean()) < 0.03
 
 
-def test_sgns_chunk_must_divide_job():
-    tok, prob, alias, syn0, syn1 = sgns_case(20, 50, 1, 5, 8, 5, 1, seed=1)
-    with pytest.raises(ValueError):
-        gpu_sgns(tok, 20, 8, 5, 1, prob, alias, syn0, syn1, 1, lanes=4, chunk_walks=300)
-
-
 def test_sgns_auto_shape():
-    lanes, chunk, streams = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
+    """The default shape is a function of the network alone (never of GPU fill or GPU count)."""
+    lanes, unit, policy = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int32(0)
+    seen = []
     for n, W in ((2300, 3465000), (38000, 152681600), (1000000, 1000000000), (3, 400)):
-        alone = None
-        for conc in (1, 3, 6):
-            _lib.call('gw_sgns_auto_shape', n, W, 1000, conc, ctypes.byref(lanes), ctypes.byref(chunk),
-                      ctypes.byref(streams))
-            assert 1 <= lanes.value <= max(1, n // 2) and 1000 % chunk.value == 0
-            assert 1 <= streams.value <= lanes.value and lanes.value <= 160 * streams.value or n < 6400
-            alone = alone or lanes.value
-            assert lanes.value <= alone and lanes.value * conc <= max(alone, 148 * 128) + conc
+        _lib.call('gw_sgns_auto_shape', n, W, 1000, ctypes.byref(lanes), ctypes.byref(unit),
+                  ctypes.byref(policy))
+        assert 1 <= lanes.value <= max(1, n // 2) and unit.value >= 1 and policy.value in (0, 1)
+        assert lanes.value * unit.value <= max(W, unit.value)
+        seen.append(lanes.value)
+    assert seen[0] <= seen[1] <= seen[2]
 
 
 # ------------------------------------------------------------------------------------------------

@@ -302,7 +302,7 @@ def test_sgns_c_oracle_matches_python_statement(merged, d):
     pure-Python statement of the same definitions, bit for bit; ragged walks, walks that step back,
     repeated negatives and negatives equal to the centre all occur on this 9-node graph."""
     from oracle import sgns_py
-    from tests import graphs
+    from genewalk_b200 import workloads as graphs
     n = 9
     row_ptr, col_idx = graphs.csr_arrays(n, 12, seed=4, self_loops=1)
     tok = olib.walk_uniform(row_ptr, col_idx, 2, 10, 3).copy()

@@ -115,48 +115,42 @@ def test_rolling_schedule_order_and_shares(monkeypatch):
     monkeypatch.setattr(torch.cuda, 'stream', fake_ctx)
     monkeypatch.setattr(R, '_side_streams', lambda count: side[:count])
     log = []
-    R._run_rolling(8, 3, lambda i, together: log.append(('enq', i, together, active[-1])) or ('job', i),
+    R._run_rolling(8, 3, lambda i: log.append(('enq', i, active[-1])) or ('job', i),
                    lambda i, job: log.append(('fin', i, job, active[-1])))
-    want = [('enq', 0, 3, 's0'), ('enq', 1, 3, 's1'), ('enq', 2, 3, 's2'),
-            ('fin', 0, ('job', 0), 's0'), ('enq', 3, 3, 's0'),
-            ('fin', 1, ('job', 1), 's1'), ('enq', 4, 3, 's1'),
-            ('fin', 2, ('job', 2), 's2'), ('enq', 5, 3, 's2'),
-            ('fin', 3, ('job', 3), 's0'), ('enq', 6, 2, 's0'),
-            ('fin', 4, ('job', 4), 's1'), ('enq', 7, 2, 's1'),
+    want = [('enq', 0, 's0'), ('enq', 1, 's1'), ('enq', 2, 's2'),
+            ('fin', 0, ('job', 0), 's0'), ('enq', 3, 's0'),
+            ('fin', 1, ('job', 1), 's1'), ('enq', 4, 's1'),
+            ('fin', 2, ('job', 2), 's2'), ('enq', 5, 's2'),
+            ('fin', 3, ('job', 3), 's0'), ('enq', 6, 's0'),
+            ('fin', 4, ('job', 4), 's1'), ('enq', 7, 's1'),
             ('fin', 5, ('job', 5), 's2'), ('fin', 6, ('job', 6), 's0'), ('fin', 7, ('job', 7), 's1')]
     assert log == want
     assert all(s.waited == ['cur'] for s in side[:3]) and cur.waited == ['s0', 's1', 's2']
     # a single stream degenerates to the serial loop on the current stream
     log.clear()
-    R._run_rolling(3, 1, lambda i, together: log.append(('enq', i, together, active[-1])) or i,
+    R._run_rolling(3, 1, lambda i: log.append(('enq', i, active[-1])) or i,
                    lambda i, job: log.append(('fin', i, job, active[-1])))
-    assert log == [('enq', 0, 1, 'cur'), ('fin', 0, 0, 'cur'), ('enq', 1, 1, 'cur'),
-                   ('fin', 1, 1, 'cur'), ('enq', 2, 1, 'cur'), ('fin', 2, 2, 'cur')]
+    assert log == [('enq', 0, 'cur'), ('fin', 0, 0, 'cur'), ('enq', 1, 'cur'),
+                   ('fin', 1, 1, 'cur'), ('enq', 2, 'cur'), ('fin', 2, 2, 'cur')]
     # more streams than units
     log.clear()
-    R._run_rolling(2, 6, lambda i, together: log.append(('enq', i, together)) or i,
+    R._run_rolling(2, 6, lambda i: log.append(('enq', i)) or i,
                    lambda i, job: log.append(('fin', i)))
-    assert log == [('enq', 0, 2), ('enq', 1, 2), ('fin', 0), ('fin', 1)]
+    assert log == [('enq', 0), ('enq', 1), ('fin', 0), ('fin', 1)]
 
 
 def test_fit_concurrent_caps_by_free_memory(monkeypatch):
-    """fit_concurrent: as many replicates at once as asked for, unless their walk corpora
-    (1.6 x 4 B x walk_length x niter x adjacency entries + 256 MiB each) exceed 85 % of the free HBM;
-    the allocator cache is only released when memory is short."""
+    """fit_concurrent: as many replicates in flight as asked for -- walks are never stored, a
+    replicate holds its tables, vocabulary and plan (64 MiB allowance + n * (8 d + 64) bytes) --
+    unless even that exceeds 80 % of the free HBM; never below one."""
     import torch
     from genewalk_b200 import replicates as R
-    state = {'free': 170 << 30, 'emptied': 0}
+    state = {'free': 170 << 30}
     monkeypatch.setattr(torch.cuda, 'mem_get_info', lambda: (state['free'], 180 << 30))
-
-    def empty():
-        state['emptied'] += 1
-        state['free'] += 8 << 30           # what the cache was holding
-    monkeypatch.setattr(torch.cuda, 'empty_cache', empty)
-    # C2: 1.53 M adjacency entries -> ~10 GB per replicate: six fit, nothing is released
-    assert R.fit_concurrent(6, 1526816) == 6 and state['emptied'] == 0
-    # C4-like: 9.8 M entries -> ~63 GB per replicate: memory is short, the cache is released, 2 fit
-    assert R.fit_concurrent(6, 9800000) == 2 and state['emptied'] == 1
-    # never below one
+    assert R.fit_concurrent(24, 38000) == 24
+    assert R.fit_concurrent(24, 1000000, 128) == 24
     state['free'] = 1 << 30
-    assert R.fit_concurrent(6, 9800000) == 1
+    assert R.fit_concurrent(24, 38000) == 11
+    state['free'] = 1 << 20
+    assert R.fit_concurrent(24, 38000) == 1
     assert R.fit_concurrent(1, 10) == 1

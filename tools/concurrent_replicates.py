@@ -11,7 +11,7 @@ import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 from genewalk_b200.csr import GraphCSR
 from genewalk_b200.deepwalk import DeepWalk
-from tests import graphs
+from genewalk_b200 import workloads as graphs
 n, u, v, is_go = graphs.human_scale_edges(seed=2)
 mode = [a for a in sys.argv[1:] if a.startswith('--')]
 sys.argv = [a for a in sys.argv if not a.startswith('--')]

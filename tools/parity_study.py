@@ -22,7 +22,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from tests import graphs  # noqa: E402
+from genewalk_b200 import workloads as graphs  # noqa: E402
 
 NITER, WL, D, K, EPOCHS = 100, 10, 8, 5, 5
 
@@ -120,7 +120,10 @@ def oracle_unit(args):
 def run_oracle(a):
     import multiprocessing as mp
     jobs = [(a.case, s, kind, r, a.mode) for s in a.seeds for kind in ('real', 'null')
-            for r in range(a.nreps)]
+            for r in range(a.nreps)
+            if not os.path.exists(os.path.join(a.out, '%s_oracle-%s_s%d_%s%d.npy' % (a.case, a.mode, s, kind, r)))]
+    if not jobs:
+        return
     with mp.Pool(min(a.procs, len(jobs))) as pool:
         for seed, kind, rep, out, dt in pool.imap_unordered(oracle_unit, jobs):
             f = os.path.join(a.out, '%s_oracle-%s_s%d_%s%d.npy' % (a.case, a.mode, seed, kind, rep))

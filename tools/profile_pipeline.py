@@ -2,7 +2,7 @@
 import os, sys, time
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
-from tests import graphs
+from genewalk_b200 import workloads as graphs
 from genewalk_b200.csr import GraphCSR
 from genewalk_b200.perform_statistics import GeneWalk
 from genewalk_b200 import replicates as R

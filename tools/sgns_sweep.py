@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT)
 from genewalk_b200 import _lib                     # noqa: E402
 from genewalk_b200.csr import GraphCSR             # noqa: E402
 from genewalk_b200.deepwalk import DeepWalk        # noqa: E402
-from tests import graphs                           # noqa: E402
+from genewalk_b200 import workloads as graphs                           # noqa: E402
 
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
 lanes_list = [int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else \

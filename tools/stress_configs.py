@@ -5,7 +5,7 @@ import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 from genewalk_b200.csr import GraphCSR
 from genewalk_b200.deepwalk import DeepWalk
-from tests import graphs
+from genewalk_b200 import workloads as graphs
 
 which = sys.argv[1]
 epochs = int(sys.argv[2]) if len(sys.argv) > 2 else 1
