@@ -1,25 +1,32 @@
 #!/usr/bin/env python
 """bench.py -- GeneWalk hot-path benchmark (contract: see the task prompt / DESIGN.md section 6).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--scale S]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--config c2|c4|c5]
 
-A "step" is one batch of 6 node_vectors replicates (cli.py:200-214; flag --replicates) -- the batch
-the replicate driver trains at once per GPU; a default GeneWalk run holds 3 + 3 independent
-trainings, the nreps=10 run of BASELINE's metric 10 + 10 -- on the human-scale synthetic gene-GO network (BASELINE.json configs[1]: ~20k genes +
-~18k GO terms, ~1M edges; reference defaults walk_length=10, niter=100, vector_size=8, window=1,
-negative=5, epochs=5): per replicate, random walks from every node (W = 100*A walks) followed by
-the 5 SGNS epochs over them (5 * 18 * W pairs).  The replicates of a step are independent; they are
-enqueued on separate CUDA streams and train concurrently on the GPU.
-metric = SGNS (centre, context) pairs trained per second of whole-stage time (walk generation,
-vocabulary, alias table and init included).
+BASELINE.json's metric is "end-to-end GeneWalk s (nreps=10) at 1/2/4/8 B200; walk steps/s; SGNS
+pairs/s".  A "step" is the representation-learning work of ONE GeneWalk run at the metric's setting
+on the human-scale synthetic gene-GO network (BASELINE.json configs[1]/[2]: ~20k genes + ~18k GO
+terms, ~1M edges; reference defaults walk_length=10, niter=100, vector_size=8, window=1, negative=5,
+epochs=5): nreps_graph = 10 real-network replicates (cli.py:200-214) and nreps_null = 10
+randomized-network replicates (cli.py:219-237) -- per replicate the vocabulary pass over its
+W = 100*A walks, the 5 SGNS epochs over them (5 * 18 * W pairs; the walks are regenerated inside the
+trainer, there is no stored corpus) and its similarity output (gene-GO cosines / null similarities).
+The 20 replicates are independent; each is enqueued on its own CUDA stream and they train
+concurrently, every one with the worker count its network calls for (gw_sgns_auto_shape: never a
+function of GPU fill or GPU count).
 
-  value   inputs (CSR) already resident in HBM, results left on the device
-  e2e     the same batch through the public API run_walks_many(nx.MultiGraph, 6): CSR extraction
-          from networkx, host->device copies, training, device->host copy of the vectors
-  N > 1   every rank runs its own replicates (the path shards by replicate); one NCCL
-          all-gather of the per-replicate gene-GO similarity vectors closes each step (weak scaling)
+  value     SGNS (centre, context) pairs per second of whole-step time; the CSR is resident in HBM
+            and the results stay on the device
+  e2e       the same metric through the public API with HOST inputs and outputs:
+            run_genewalk(nx.MultiGraph, genes, nreps 10/10) -> results DataFrame (CSR extraction,
+            H2D, all replicates, D2H of similarities, statistics)
+  pipeline  BASELINE's first metric: seconds of node_vectors + null_distribution + statistics at
+            nreps 10/10 with the 20 replicates SHARDED over the N ranks (strong scaling), plus a
+            checksum of the pooled null distribution that must agree on all ranks (it exercises the
+            variable-length NCCL exchange)
+  N > 1     value / e2e: every rank runs its own step (weak scaling, no data-path collective)
   --impl reference   the reference's CPU path for the same step restated in C (oracle/, gensim-
-          faithful SGNS, OpenMP Hogwild on all host cores) on a bounded sample of the same corpus
+            faithful SGNS, OpenMP Hogwild on all host cores) on a bounded sample of the same corpus
 """
 import argparse
 import json
@@ -33,11 +40,13 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')   # one hardware queue per replicate stream
 
 NITER, WL, D, K, EPOCHS = 100, 10, 8, 5, 5
+PAIRS_PER_WALK = 2 * (WL - 1) * EPOCHS
 BYTES_PER_PAIR = 4 * D * (2 * K + 4) + 8 + 8 * K      # 496 at d=8, K=5
 BYTES_PER_STEP = 16                                     # walk step
-METRIC = 'SGNS pairs/s over the node_vectors stage (walks + 5 SGNS epochs per replicate)'
+METRIC = 'SGNS pairs/s over the replicates of a GeneWalk run (nreps_graph = nreps_null = 10)'
 
 
 # ---------------------------------------------------------------------------------------------
@@ -83,14 +92,40 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def build_inputs(scale):
-    from genewalk_b200 import workloads as graphs
-    ng, ngo = int(20000 * scale), int(18000 * scale)
-    n, u, v, is_go = graphs.human_scale_edges(seed=2, n_genes=ng, n_go=ngo,
-                                              n_gene_edges=int(700000 * scale),
-                                              n_annot=int(250000 * scale), n_isa=int(50000 * scale),
-                                              n_modules=max(4, int(500 * scale)))
-    return graphs, n, u, v, is_go, ng
+def build_inputs(args):
+    """(config name, n, u, v, is_go | None, n_genes | None)."""
+    from genewalk_b200 import workloads
+    if args.config == 'c4':
+        return (workloads,) + workloads.indra_scale_edges(seed=3) + (None, None)
+    if args.config == 'c5':
+        return (workloads,) + workloads.power_law_stress_edges(seed=4) + (None, None)
+    s = args.scale
+    ng, ngo = int(20000 * s), int(18000 * s)
+    n, u, v, is_go = workloads.human_scale_edges(seed=2, n_genes=ng, n_go=ngo,
+                                                 n_gene_edges=int(700000 * s), n_annot=int(250000 * s),
+                                                 n_isa=int(50000 * s), n_modules=max(4, int(500 * s)))
+    return workloads, n, u, v, is_go, ng
+
+
+WORKLOADS = {
+    'c2': 'human-scale synthetic gene-GO network (BASELINE.json configs[1]/[2]): one GeneWalk run, '
+          '%d real + %d null node_vectors replicates in flight on the GPU',
+    'c4': 'INDRA-scale dense synthetic multigraph (BASELINE.json configs[3]: 50k nodes, 5M multi-edges, '
+          'Pareto degrees): %d real + %d null node_vectors replicates in flight on the GPU',
+    'c5': '1M-node power-law stress graph (BASELINE.json configs[4]): %d real + %d null node_vectors '
+          'replicates in flight on the GPU'}
+
+
+def workload_config(args, n, n_edges, A):
+    return {'workload': WORKLOADS[args.config] % (args.real, args.null), 'config': args.config,
+            'nodes': n, 'edges': n_edges, 'adjacency_entries': A, 'walks_per_real_replicate': NITER * A,
+            'real_replicates_per_step': args.real, 'null_replicates_per_step': args.null,
+            'walk_length': WL, 'niter': NITER, 'vector_size': D, 'window': 1, 'negative': K,
+            'epochs': EPOCHS, 'scale': args.scale,
+            'l2': 'L2 is flushed between timed steps (a 512 MB buffer is written); every step rebuilds '
+                  'its %d table pairs from scratch and draws new walks (new seeds).  Within a step the '
+                  'tables are L2-resident BY DESIGN (that residency is what the kernel is built on, '
+                  'not a carry-over between iterations)' % (args.real + args.null)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -108,24 +143,23 @@ def cpu_sample_rate(row_ptr, col_idx, threads, target_s=15.0):
         return time.perf_counter() - t0
     pilot = min(W, 20000 * max(1, threads))
     dt = run(pilot)
-    rate = pilot * 2 * (WL - 1) * EPOCHS / dt
-    m = int(min(W, max(pilot, rate * target_s / (2 * (WL - 1) * EPOCHS))))
+    rate = pilot * PAIRS_PER_WALK / dt
+    m = int(min(W, max(pilot, rate * target_s / PAIRS_PER_WALK)))
     if m > pilot:
         dt = run(m)
     else:
         m = pilot
-    pairs = m * 2 * (WL - 1) * EPOCHS
-    return pairs / dt, ('first %d of %d walks of the corpus (reference order), %d epochs = %.1f M '
-                        'pairs in %.1f s' % (m, W, EPOCHS, pairs / 1e6, dt))
+    pairs = m * PAIRS_PER_WALK
+    return pairs / dt, ('first %d of %d walks of one replicate\'s corpus (reference order), %d epochs = '
+                        '%.1f M pairs in %.1f s' % (m, W, EPOCHS, pairs / 1e6, dt))
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    graphs, n, u, v, is_go, ng = build_inputs(args.scale)
-    row_ptr, col_idx = graphs.csr_from_edges_numpy(n, u, v)
-    from oracle import lib as olib
+    workloads, n, u, v, is_go, ng = build_inputs(args)
+    row_ptr, col_idx = workloads.csr_from_edges_numpy(n, u, v)
     threads = host_threads()   # torchrun exports OMP_NUM_THREADS=1: ask the OS instead
     vals, sample = [], ''
     t_all = time.perf_counter()
@@ -136,42 +170,53 @@ def run_reference(args):
             vals.append(rate)
     value = float(np.mean(vals))
     A = int(row_ptr[-1])
-    pairs_step = args.replicates * NITER * A * 2 * (WL - 1) * EPOCHS
+    # a null replicate's corpus is ~1.28x a real one's; the extrapolation uses the real size for all
+    pairs_step = (args.real + args.null) * NITER * A * PAIRS_PER_WALK
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'pairs/s',
             'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': 1e3 * pairs_step / value, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': workload_config(n, len(u), A, args.scale, args.replicates),
+            'config': workload_config(args, n, len(u), A),
             'cpu_baseline': {'value': value, 'unit': 'pairs/s', 'cores': threads, 'kind': 'port',
                              'sample': sample},
             'e2e': {'value': value, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0,
                     'd2h_bytes_per_step': 0},
-            'note': 'ms_per_step is the full-stage time extrapolated linearly from the sample; '
+            'note': 'ms_per_step is the full-step time extrapolated linearly from the sample; '
                     'gensim is not installable here, the C oracle restates it (oracle/gw_oracle.c)',
             'wall_s': time.perf_counter() - t_all}
     emit(line)
 
 
-def workload_config(n, n_edges, A, scale, reps):
-    return {'workload': 'human-scale synthetic gene-GO network, batch of %d node_vectors replicates '
-                        'trained concurrently (BASELINE.json configs[1])' % reps,
-            'nodes': n, 'edges': n_edges, 'adjacency_entries': A, 'walks_per_replicate': NITER * A,
-            'replicates_per_step': reps,
-            'walk_length': WL, 'niter': NITER, 'vector_size': D, 'window': 1, 'negative': K,
-            'epochs': EPOCHS, 'pairs_per_step': reps * NITER * A * 2 * (WL - 1) * EPOCHS,
-            'scale': scale,
-            'l2': 'token streams (%.1f GB per replicate) >> 126 MB L2; embedding tables are rebuilt '
-                  'every step' % (NITER * A * WL * 4 / 1e9)}
-
-
 # ---------------------------------------------------------------------------------------------
+def live_l2_peak(rows):
+    """Build tools/l2_mixbench.cu with nvcc and measure, on this GPU and in this run, the rate of the
+    SGNS step's access pattern (13 gathers + 14 reductions of 32-byte rows per step, groups of 4
+    lanes) over `rows` uniformly drawn rows -- the L2 request-rate ceiling for that mix.  Returns
+    (steps/s, gathers-only steps/s, source text) or (None, None, why)."""
+    exe = os.path.join(ROOT, 'gpurun_out', 'l2_mixbench_r02')
+    try:
+        os.makedirs(os.path.dirname(exe), exist_ok=True)
+        nvcc = '/usr/local/cuda/bin/nvcc' if os.path.exists('/usr/local/cuda/bin/nvcc') else 'nvcc'
+        subprocess.run([nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-o', exe,
+                        os.path.join(ROOT, 'tools', 'l2_mixbench.cu')], check=True, capture_output=True,
+                       timeout=300)
+        out = subprocess.run([exe, '--peak', str(int(rows))], check=True, capture_output=True, text=True,
+                             timeout=300).stdout
+        recs = [json.loads(x) for x in out.splitlines() if x.startswith('{')]
+        mix = max(r['steps_per_s'] for r in recs if r['reds'] == 14)
+        gat = max(r['steps_per_s'] for r in recs if r['reds'] == 0)
+        return mix, gat, 'measured in this run (tools/l2_mixbench.cu --peak %d)' % rows
+    except Exception as exc:   # no nvcc on this box, or the tool failed
+        return None, None, 'live measurement failed (%s)' % (str(exc)[:80],)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from genewalk_b200 import _lib
     from genewalk_b200.csr import GraphCSR
-    from genewalk_b200.deepwalk import DeepWalk
-    from genewalk_b200.replicates import run_walks_many
+    from genewalk_b200.replicates import (_NullJob, _run_rolling, fit_concurrent, preload_kernels,
+                                          real_replicate, run_genewalk)
     from genewalk_b200.perform_statistics import GeneWalk
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -187,55 +232,77 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    graphs, n, u, v, is_go, ng = build_inputs(args.scale)
-    mg, genes = graphs.edges_to_networkx(n, u, v, is_go, ng)
-    csr = GraphCSR.from_networkx(mg).to_device()
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    workloads, n, u, v, is_go, ng = build_inputs(args)
+    mg = genes = None
+    if is_go is not None:
+        mg, genes = workloads.edges_to_networkx(n, u, v, is_go, ng)
+        csr = GraphCSR.from_networkx(mg).to_device()
+        from genewalk_b200.csr import multigraph_degrees
+        degrees = multigraph_degrees(mg)
+        gw = GeneWalk(mg, genes, [], np.zeros(1, np.float32), gene_id_type='custom')
+        pairs = gw.collect_pairs()
+        d_pg = torch.from_numpy(pairs['pair_gene'].astype(np.int32)).cuda()
+        d_po = torch.from_numpy(pairs['pair_go'].astype(np.int32)).cuda()
+    else:   # C4 / C5: no GO attributes; the replicate's product is its table
+        rp, ci = workloads.csr_from_edges_numpy(n, u, v)
+        csr = GraphCSR(['v%d' % i for i in range(n)], rp, ci).to_device()
+        degrees = workloads.multigraph_degrees_from_edges(n, u, v)
+        d_pg = d_po = None
+    m_pairs = int(d_po.numel()) if d_po is not None else 0
     A = csr.nnz
-    W = NITER * A
-    R = max(1, int(args.replicates))
-    pairs_step = R * W * 2 * (WL - 1) * EPOCHS
-    gw = GeneWalk(mg, genes, [], np.zeros(1, np.float32), gene_id_type='custom')
-    pairs = gw.collect_pairs()
-    d_pg = torch.from_numpy(pairs['pair_gene'].astype(np.int32)).cuda()
-    d_po = torch.from_numpy(pairs['pair_go'].astype(np.int32)).cuda()
-    m_pairs = int(d_po.numel())
-    gathered = [torch.empty((R, m_pairs), dtype=torch.float32, device='cuda') for _ in range(world)]
-    sims_all = torch.empty((R, m_pairs), dtype=torch.float32, device='cuda')
-    cur = torch.cuda.current_stream()
-    side = [torch.cuda.Stream() for _ in range(R)] if R > 1 else [cur]
-    train_events, walk_events = [], []
+    R_real, R_null = args.real, args.null
+    R = R_real + R_null
+    w2v = dict(lanes=args.lanes) if args.lanes else {}
+    preload_kernels(D, **w2v)
+    in_flight = fit_concurrent(R, n, D, NITER * A, args.lanes)
+    train_events, count_events = [], []
+    l2_flush = torch.empty(512 << 20, dtype=torch.uint8, device='cuda')
 
     def device_step(step, timed):
-        """R independent replicates, one per CUDA stream, then the exchange of their products."""
-        dvs = []
-        for k in range(R):
-            if R > 1:
-                side[k].wait_stream(cur)
-            with torch.cuda.stream(side[k]):
-                def hook(ep, when):
-                    e = torch.cuda.Event(enable_timing=True)
-                    e.record()
-                    train_events.append((len(dvs), ep, when, e))
-                seed = ((1 + step) * 1000003 + rank) * 16 + k
-                dw = DeepWalk(csr, WL, NITER, seed=seed)
-                w0 = torch.cuda.Event(enable_timing=True); w1 = torch.cuda.Event(enable_timing=True)
-                w0.record()
-                dw.get_walks()
-                w1.record()
-                if timed:
-                    walk_events.append((w0, w1))
-                dv = dw.train_device(vector_size=D, negative=K, epochs=EPOCHS, lanes=args.lanes,
-                                     concurrent=R, epoch_hook=hook if timed else None)
-                # the replicate's product in the pipeline: gene-GO similarities (fixed length)
-                _lib.call('gw_cosine_pairs', D, _lib.ptr(dv['syn0']), m_pairs, _lib.ptr(d_pg),
-                          _lib.ptr(d_po), _lib.ptr(sims_all[k]), _lib.stream_ptr())
-                dvs.append(dv)
-        if R > 1:
-            for k in range(R):
-                cur.wait_stream(side[k])
-        if world > 1:
-            dist.all_gather(gathered, sims_all)
-        return dvs
+        """R independent replicates, one per CUDA stream; returns the walks trained."""
+        walks = []
+        base = (1 + step) * 1000003 + rank
+
+        def hook_for(unit):
+            def hook(stage, when):
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                (count_events if stage == 'count' else train_events).append((unit, stage, when, e))
+            return hook if timed else None
+
+        def enqueue(i):   # longest first: the null replicates (1.28x the walks), then the real ones
+            if i >= R_null:
+                dw = real_replicate(csr, base, i - R_null, D, wait=False, epoch_hook=hook_for(i), **w2v)
+                if m_pairs:   # the replicate's product in the pipeline: gene-GO similarities
+                    sims = torch.empty(m_pairs, dtype=torch.float32, device='cuda')
+                    _lib.call('gw_cosine_pairs', D, _lib.ptr(dw._pending['syn0']), m_pairs, _lib.ptr(d_pg),
+                              _lib.ptr(d_po), _lib.ptr(sims), _lib.stream_ptr())
+                walks.append(dw._pending['W'])
+                return dw
+            job = _NullJob(None, base, i, D, WL, NITER, dict(epoch_hook=hook_for(i), **w2v),
+                           degrees=degrees)
+            walks.append(len(job.dw.walks))
+            return job
+
+        def finish(i, job):
+            if i < R_null:
+                job.finish()           # the null similarities of the replicate (device)
+            else:
+                job._pending = None
+        _run_rolling(R, in_flight, enqueue, finish)
+        return walks, (1 + step)
 
     # ---- value: device-resident ------------------------------------------------------------
     for i in range(args.warmup):
@@ -246,141 +313,200 @@ def run_ours(args):
     launches0 = _lib.launch_count()
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
+    walks_timed = 0
     for i in range(args.steps):
-        dv = device_step(args.warmup + i, True)[0]
+        l2_flush.fill_(i)          # nothing of the previous step stays in L2
+        wk, _ = device_step(args.warmup + i, True)
+        walks_timed += sum(wk)
     t1.record()
     barrier()
     launches = _lib.launch_count() - launches0
     clocks = mon.stop()
-    ms = t0.elapsed_time(t1)
-    t_ms = torch.tensor([ms], dtype=torch.float64, device='cuda')
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_max = float(t_ms.item())
-    value = world * pairs_step * args.steps / (ms_max / 1e3)
-    # dominant kernel: one SGNS epoch launch.  With R > 1 the launches of different replicates
-    # overlap on the GPU, so the rate is (launches' pairs) / (time during which at least one SGNS
-    # launch was in flight), from the per-launch CUDA events on the launching streams.
-    befores = [e for _, ep, when, e in train_events if when == 'before']
-    afters = [e for _, ep, when, e in train_events if when == 'after']
-    k_ms = [b.elapsed_time(a) for b, a in zip(befores, afters)]
-    k_avg = float(np.mean(k_ms)) if k_ms else float('nan')
-    spans = sorted((t0.elapsed_time(b), t0.elapsed_time(a)) for b, a in zip(befores, afters))
+    ms_max = max_over_ranks(t0.elapsed_time(t1))
+    pairs_timed_all = sum_over_ranks(walks_timed * PAIRS_PER_WALK)
+    value = pairs_timed_all / (ms_max / 1e3)
+    # dominant kernel: one SGNS epoch launch.  The launches of the replicates of a step overlap on
+    # the GPU, so the rate is (launches' pairs) / (time during which at least one SGNS launch was in
+    # flight), from the per-launch CUDA events on the launching streams.
+    # (events of different steps share (unit, stage) keys: they are paired in recording order)
+    spans, k_ms, open_ev = [], [], {}
+    for uid, st, when, e in train_events:
+        if when == 'before':
+            open_ev[(uid, st)] = e
+        else:
+            b = open_ev.pop((uid, st))
+            k_ms.append(b.elapsed_time(e))
+            spans.append((t0.elapsed_time(b), t0.elapsed_time(e)))
+    if os.environ.get('GW_BENCH_SPANS'):   # diagnosis: (unit, stage, begin ms, end ms) of every launch
+        rec, op = [], {}
+        for uid, st, when, e in count_events + train_events:
+            if when == 'before':
+                op[(uid, st)] = e
+            else:
+                rec.append([uid, st, t0.elapsed_time(op.pop((uid, st))), t0.elapsed_time(e)])
+        with open(os.environ['GW_BENCH_SPANS'], 'w') as f:
+            json.dump(rec, f)
+    spans.sort()
     busy_ms, hi = 0.0, -1.0
     for lo, up in spans:
         if up > hi:
             busy_ms += up - max(lo, hi)
             hi = up
     n_launch = len(spans)
-    walk_ms = float(np.mean([a.elapsed_time(b) for a, b in walk_events]))
-    pairs_launch = W * 2 * (WL - 1)
+    k_avg = float(np.mean(k_ms)) if k_ms else float('nan')
     k_eff = busy_ms / max(n_launch, 1)            # GPU time per launch with the overlap credited
-    achieved = BYTES_PER_PAIR * pairs_launch / (k_eff / 1e3) / 1e9
+    pairs_launch_avg = walks_timed * 2 * (WL - 1) / max(n_launch / EPOCHS, 1)
+    achieved = BYTES_PER_PAIR * walks_timed * PAIRS_PER_WALK / (busy_ms / 1e3) / 1e9
+    c_open, c_ms = {}, []
+    for uid, st, when, e in count_events:
+        if when == 'before':
+            c_open[uid] = e
+        else:
+            c_ms.append(c_open.pop(uid).elapsed_time(e))
     peaks = {}
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
             peaks = json.load(f)
     except Exception:
         pass
-    peak = float(peaks.get('hbm_gbs', 6650.0))
-    traffic = None
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    traffic, traffic_src = None, None
     try:
-        with open(os.path.join(ROOT, 'profiles', 'sgns_train_traffic.json')) as f:
-            traffic = json.load(f).get('dram_bytes_per_launch')
+        with open(os.path.join(ROOT, 'profiles', 'r02_sgns_train_traffic.json')) as f:
+            tj = json.load(f)
+            traffic, traffic_src = tj.get('dram_bytes_per_launch'), tj.get('source')
     except Exception:
         pass
+    dv_shape = None
 
-    l2_peaks = {}
-    try:
-        with open(os.path.join(ROOT, 'profiles', 'l2_pattern_peaks.json')) as f:
-            l2_peaks = json.load(f)
-    except Exception:
-        pass
-
-    # ---- e2e: public API with host inputs ---------------------------------------------------
-    barrier()
-    d2h = 0
-    h2d = csr.row_ptr.nbytes + csr.col_idx.nbytes + R * n * D * 4
-    for i in range(min(args.warmup, 1)):
-        run_walks_many(mg, R, base_seed=7 + i, concurrent=R, lanes=args.lanes)
-    barrier()
-    e0 = time.perf_counter()
-    for i in range(args.steps):
-        dws = run_walks_many(mg, R, base_seed=100 + i * world + rank, concurrent=R, lanes=args.lanes)
-        d2h = 0
-        for dw in dws:
-            wv = dw.model.wv
-            d2h += (wv.vectors.nbytes + dw.model.syn1neg.nbytes + wv.counts.nbytes +
-                    wv.node_ids.nbytes)
+    # ---- pipeline (strong scaling) and e2e (public API, host inputs) -------------------------
+    pipeline = e2e = None
+    if mg is not None and not args.no_pipeline:
+        run_genewalk(mg, genes, nreps_graph=1, nreps_null=1, alpha_fdr=0.1, gene_id_type='custom',
+                     base_seed=99, shard=False, **w2v)        # host-side warm-up of the public path
+        barrier()
+        p0 = time.perf_counter()
+        df, parts = run_genewalk(mg, genes, nreps_graph=args.real, nreps_null=args.null, alpha_fdr=0.1,
+                                 gene_id_type='custom', base_seed=2024, return_parts=True, **w2v)
+        torch.cuda.synchronize()
+        local_s = time.perf_counter() - p0
+        barrier()
+        p_s = max_over_ranks(local_s)
+        p_pairs = sum_over_ranks(parts['walks_trained_local'] * PAIRS_PER_WALK)
+        null = parts['null']
+        chk = float(np.float64(null.astype(np.float64).sum())) if len(null) else 0.0
+        chk_t = torch.tensor([chk, float(len(null)), float(len(df))], dtype=torch.float64, device='cuda')
+        chks = [torch.empty_like(chk_t) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(chks, chk_t)
+        else:
+            chks = [chk_t]
+        same = all(bool(torch.equal(c, chks[0])) for c in chks)
+        pipeline = {'nreps_graph': args.real, 'nreps_null': args.null, 'seconds': p_s,
+                    'scaling': 'strong', 'pairs': p_pairs, 'pairs_per_s': p_pairs / p_s,
+                    'rows_significant': int(len(df)), 'alpha_fdr': 0.1,
+                    'pooled_null': {'n': int(len(null)), 'sum': chk, 'equal_on_all_ranks': bool(same)},
+                    'timings_rank0': parts['timings'],
+                    'timeline_rank0_s': [[u[0], u[1], k, round(b / 1e3, 1), round(e / 1e3, 1)]
+                                         for u, k, b, e in parts['timeline']],
+                    'limiter': 'replicates are independent and run concurrently; a training uses the '
+                               'worker count its network calls for (fidelity), so with fewer replicates '
+                               'per GPU the per-worker latency, not the GPU, bounds the time'}
+        # e2e: weak scaling like `value` -- every rank runs a whole GeneWalk run of its own
+        # CSR + (gene, GO) index arrays + gensim's initial rows (uploaded once, shared by all
+        # replicates) + the degree sequence of every randomization
+        h2d = csr.row_ptr.nbytes + csr.col_idx.nbytes + 2 * 4 * m_pairs + n * D * 4 + R_null * 4 * n
+        if world == 1:
+            e_s, e_pairs, d2h = p_s, p_pairs, int(parts['sims'].numel() * 4 + null.nbytes)
+        else:
+            barrier()
+            e0 = time.perf_counter()
+            df2, parts2 = run_genewalk(mg, genes, nreps_graph=args.real, nreps_null=args.null,
+                                       alpha_fdr=0.1, gene_id_type='custom', base_seed=3000 + rank,
+                                       return_parts=True, shard=False, **w2v)
+            torch.cuda.synchronize()
+            local_e = time.perf_counter() - e0
+            barrier()
+            e_s = max_over_ranks(local_e)
+            e_pairs = sum_over_ranks(parts2['walks_trained_local'] * PAIRS_PER_WALK)
+            d2h = int(parts2['sims'].numel() * 4 + parts2['null'].nbytes)
+        e2e = {'value': e_pairs / e_s, 'unit': 'pairs/s', 'h2d_bytes_per_step': int(h2d),
+               'd2h_bytes_per_step': int(d2h), 'ms_per_step': 1e3 * e_s,
+               'what': 'run_genewalk(nx.MultiGraph, genes, nreps_graph=%d, nreps_null=%d) -> DataFrame, '
+                       'one whole run per rank' % (args.real, args.null)}
+    elif mg is None:
+        # C4 / C5: no GeneWalk table to make; e2e = the same step from HOST CSR arrays to host vectors
+        from genewalk_b200.replicates import run_walks_many
+        host_csr = GraphCSR(csr.nodes, csr.row_ptr, csr.col_idx)
+        barrier()
+        e0 = time.perf_counter()
+        dws = run_walks_many(host_csr, R, base_seed=555 + rank, **w2v)
+        torch.cuda.synchronize()
+        local_e = time.perf_counter() - e0
+        barrier()
+        e_s = max_over_ranks(local_e)
+        e_pairs = sum_over_ranks(sum(len(dw.walks) for dw in dws) * PAIRS_PER_WALK)
+        e2e = {'value': e_pairs / e_s, 'unit': 'pairs/s',
+               'h2d_bytes_per_step': int(csr.row_ptr.nbytes + csr.col_idx.nbytes + n * D * 4),
+               'd2h_bytes_per_step': int(sum(2 * dw.model.wv.vectors.nbytes for dw in dws)),
+               'ms_per_step': 1e3 * e_s,
+               'what': 'run_walks_many(host CSR, %d replicates) -> host vectors' % R}
         del dws
-    barrier()
-    e_s = time.perf_counter() - e0
-    t_e = torch.tensor([e_s], dtype=torch.float64, device='cuda')
-    if world > 1:
-        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_value = world * pairs_step * args.steps / float(t_e.item())
 
     line = None
     if rank == 0:
+        import ctypes
+        a_l, a_u, a_p = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int32(0)
+        _lib.call('gw_sgns_auto_shape', n, NITER * A, 1000, ctypes.byref(a_l), ctypes.byref(a_u),
+                  ctypes.byref(a_p))
+        mix, gat, src = live_l2_peak(2 * R * n) if not args.no_l2_peak else (None, None, 'skipped')
+        steps_per_s = walks_timed * PAIRS_PER_WALK / 2 / (busy_ms / 1e3)   # step = 2 pairs (13 gathers + 14 reductions)
+        if mix is None:
+            try:
+                with open(os.path.join(ROOT, 'profiles', 'l2_pattern_peaks.json')) as f:
+                    mix = json.load(f)['uniform_rows']
+                    src += '; fallback: profiles/l2_pattern_peaks.json (round 1, one 38k-row table)'
+            except Exception:
+                pass
+        peak_gbs = mix * 2 * BYTES_PER_PAIR / 1e9 if mix else None
         line = {'metric': METRIC, 'value': value, 'unit': 'pairs/s', 'n_gpus': world,
                 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_max / args.steps,
                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-                'data': 'synthetic', 'config': workload_config(n, len(u), A, args.scale, R),
-                'clocks': clocks,
-                'e2e': {'value': e2e_value, 'unit': 'pairs/s', 'h2d_bytes_per_step': int(h2d),
-                        'd2h_bytes_per_step': int(d2h), 'ms_per_step': 1e3 * float(t_e.item()) / args.steps},
-                'gpu_launches': int(launches),
-                'roofline': {'kernel': 'sgns_train_kernel<8,4,5> (one epoch per launch)',
-                             'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                             'frac': achieved / peak, 'traffic': traffic,
-                             'peak_source': 'measured (MEASURED_PEAKS.json hbm_gbs)' if peaks else 'fallback',
+                'data': 'synthetic', 'config': workload_config(args, n, len(u), A),
+                'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
+                'roofline': {'kernel': 'sgns_train_kernel<8,4,5> (one epoch of one replicate per launch)',
+                             'bound': 'l2', 'achieved': achieved, 'peak': peak_gbs, 'unit': 'GB/s',
+                             'frac': achieved / peak_gbs if peak_gbs else None, 'traffic': traffic,
+                             'traffic_source': traffic_src,
+                             'peak_source': src,
+                             'peak_pattern_steps_per_s': mix, 'peak_gathers_only_steps_per_s': gat,
+                             'achieved_steps_per_s': steps_per_s,
+                             'frac_of_hbm_copy_bw': achieved / hbm_peak,
+                             'hbm_peak_gbs': hbm_peak,
                              'algorithmic_bytes_per_pair': BYTES_PER_PAIR,
-                             'pairs_per_launch': pairs_launch, 'avg_launch_ms': k_eff,
-                             'launches': n_launch, 'concurrent_launches': R,
+                             'pairs_per_launch': pairs_launch_avg, 'avg_launch_ms': k_eff,
+                             'launches': n_launch, 'replicates_in_flight': in_flight,
                              'launch_ms_on_its_stream': k_avg, 'sgns_busy_ms': busy_ms,
-                             'note': 'avg_launch_ms = (time with >= 1 SGNS launch in flight) / '
-                                     'launches: the launches of the R replicates of a step overlap. '
-                                     'Tables are L2-resident by design: the algorithmic bytes are '
-                                     'L2 sector traffic; HBM carries only the token streams'},
-                'roofline_l2': {
-                    'what': 'SGNS steps/s (2 pairs) vs the measured rate of the same gather+reduce '
-                            'pattern in isolation (tools/l2_mixbench.cu, profiles/l2_pattern_peaks.json)',
-                    'achieved_steps_per_s': pairs_launch / 2 / (k_eff / 1e3),
-                    'peak_uniform_rows': l2_peaks.get('uniform_rows'),
-                    'peak_c2_row_popularity': l2_peaks.get('c2_popularity'),
-                    'frac_of_uniform': (pairs_launch / 2 / (k_eff / 1e3) / l2_peaks['uniform_rows'])
-                    if l2_peaks.get('uniform_rows') else None},
-                'walk': {'steps_per_s': W * (WL - 1) / (walk_ms / 1e3), 'ms': walk_ms,
-                         'achieved_gbs': BYTES_PER_STEP * W * (WL - 1) / (walk_ms / 1e3) / 1e9,
-                         'frac_of_l2_random_sector_rate':
-                             (W * (WL - 1) / (walk_ms / 1e3) / l2_peaks['random_sector_gathers_per_s'])
-                             if l2_peaks.get('random_sector_gathers_per_s') else None,
-                         'note': 'timed on its stream while the other replicates of the step train; '
-                                 'one random L2 sector (the neighbour) per step is the bound'},
-                'sgns_kernel_pairs_per_s': pairs_launch / (k_eff / 1e3),
-                'sgns_shape': {'lanes': dv['lanes'], 'chunk_walks': dv['chunk_walks'], 'streams': dv['streams'],
-                               'job_walks': dv['job_walks']}}
-    if args.pipeline > 0:
-        # BASELINE metric, first item: end-to-end seconds of node_vectors + null_distribution +
-        # statistics (cli.py:194-252) with nreps_graph = nreps_null = --pipeline, replicates sharded
-        from genewalk_b200.replicates import run_genewalk
-        barrier()
-        p0 = time.perf_counter()
-        df, parts = run_genewalk(mg, genes, nreps_graph=args.pipeline, nreps_null=args.pipeline,
-                                 alpha_fdr=0.1, gene_id_type='custom', base_seed=2024,
-                                 lanes=args.lanes, concurrent=R, return_parts=True)
-        barrier()
-        t_p = torch.tensor([time.perf_counter() - p0], dtype=torch.float64, device='cuda')
-        if world > 1:
-            dist.all_reduce(t_p, op=dist.ReduceOp.MAX)
-        if rank == 0:
-            line['pipeline'] = {'nreps_graph': args.pipeline, 'nreps_null': args.pipeline,
-                                'seconds': float(t_p.item()), 'rows_significant': int(len(df)),
-                                'alpha_fdr': 0.1, 'timings_rank0': parts['timings'],
-                                'timeline_rank0_ms': [[u[0], u[1], k, round(b), round(e)]
-                                                      for u, k, b, e in parts['timeline']]}
+                             'note': 'the embedding tables are L2-resident by design, so the 496 B/pair '
+                                     'are L2 sector traffic (HBM carries almost nothing: see traffic); '
+                                     'peak = 2*496 B x the measured rate of the step\'s own request mix '
+                                     '(13 row gathers + 14 row reductions) over uniformly drawn rows; '
+                                     'avg_launch_ms = (time with >= 1 SGNS launch in flight) / launches '
+                                     'because the launches of a step overlap'},
+                'walk': {'kernel': 'walk_count_smem_kernel (vocabulary pass: every walk drawn, counted, '
+                                   'not stored)',
+                         'steps_per_s': (NITER * A * (WL - 1) / (float(np.mean(c_ms)) / 1e3)) if c_ms else None,
+                         'ms_on_its_stream': float(np.mean(c_ms)) if c_ms else None,
+                         'note': 'timed on its stream while the other replicates of the step train; the '
+                                 'trainer draws the same walks again in every epoch inside the SGNS '
+                                 'kernel (12 algorithmic bytes per step, nothing stored)'},
+                'sgns_kernel_pairs_per_s': walks_timed * PAIRS_PER_WALK / (busy_ms / 1e3),
+                'sgns_shape': {'lanes': a_l.value if not args.lanes else args.lanes,
+                               'unit_walks': a_u.value, 'policy': ('chunk', 'burst')[a_p.value],
+                               'job_walks': 1000, 'per_replicate': True}}
+        if pipeline is not None:
+            line['pipeline'] = pipeline
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import lib as olib
         csr.to_host()
         threads = host_threads()
         rate, sample = cpu_sample_rate(csr.row_ptr, csr.col_idx, threads)
@@ -416,17 +542,24 @@ def emit(line):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=2)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--scale', type=float, default=1.0, help='shrink the workload (tests only)')
-    ap.add_argument('--lanes', type=int, default=0, dest='lanes')
-    ap.add_argument('--replicates', type=int, default=6,
-                    help='replicates per step, trained concurrently on one GPU')
+    ap.add_argument('--config', default='c2', choices=['c2', 'c4', 'c5'],
+                    help='c2: the headline workload (default); c4 / c5: BASELINE.json configs[3] / [4]')
+    ap.add_argument('--scale', type=float, default=1.0, help='shrink the c2 workload (tests only)')
+    ap.add_argument('--lanes', type=int, default=0, help='workers per training (0: library default)')
+    ap.add_argument('--real', type=int, default=None, help='real-network replicates per step')
+    ap.add_argument('--null', type=int, default=None, help='randomized-network replicates per step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--pipeline', type=int, default=0,
-                    help='also time the full pipeline with this many real and null replicates')
+    ap.add_argument('--no-pipeline', action='store_true')
+    ap.add_argument('--no-l2-peak', action='store_true')
     args = ap.parse_args()
+    default_reps = {'c2': (10, 10), 'c4': (2, 2), 'c5': (2, 2)}[args.config]
+    if args.real is None:
+        args.real = default_reps[0]
+    if args.null is None:
+        args.null = default_reps[1]
     if args.warmup < 3 and args.impl == 'ours' and args.scale == 1.0:
         print('warning: fewer than 3 warm-up steps', file=sys.stderr)
     quiet_stdout()

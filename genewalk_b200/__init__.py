@@ -8,8 +8,16 @@ Drop-in modules (same names, signatures and error behaviour as /root/reference/g
 All arithmetic runs in libgenewalk_b200.so (C ABI: include/genewalk_b200.h); no CPU fallback.
 """
 import logging
+import os
 
-__version__ = '0.1.0'
+__version__ = '0.2.0'
+
+# The replicate driver keeps up to 24 independent trainings in flight on as many CUDA streams.  A
+# CUDA context has 8 hardware work queues by default; streams beyond that share queues, and a
+# seconds-long training kernel then holds back the kernels of the streams queued behind it
+# (measured: 12 streams ran as 8 + 4).  32 is the maximum; it must be set before the CUDA context
+# is created, so import this package before the first CUDA call of the process (or export it).
+os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')
 
 logging.getLogger('genewalk').addHandler(logging.NullHandler())
 

@@ -49,6 +49,8 @@ SIGNATURES = {
 
 # functions that do not return a gw_status
 INT64_RETURNS = {'gw_sgns_plan_capacity': [_i32, _i64, _i64, _i32]}
+# plain int results that are not a gw_status
+INT_RETURNS = {'gw_sgns_resident_trainings': [_i32, _i64]}
 ABI_VERSION = 200   # GW_VERSION of include/genewalk_b200.h this binding was written against
 
 _lib = None
@@ -85,6 +87,10 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = ctypes.c_int64
+    for name, argtypes in INT_RETURNS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = ctypes.c_int
     lib.gw_last_error.argtypes = []
     lib.gw_last_error.restype = ctypes.c_char_p
     lib.gw_launch_count.argtypes = []

@@ -81,8 +81,11 @@ def build_parser():
     parser.add_argument('--dim_rep', default=8, type=int)
     parser.add_argument('--save_dw', default=False, type=bool)
     parser.add_argument('--random_seed', default=None, type=int)
+    parser.add_argument('--go_obo', default=None,
+                        help='GPU build only: GO OBO file for the GO node names / domains of a '
+                             'sif_full network with custom ids (read without the reference package).')
     parser.add_argument('--concurrent', default=DEFAULT_CONCURRENT, type=int,
-                        help='GPU build only: replicates trained at once on one GPU.')
+                        help='GPU build only: replicates in flight at once on one GPU (does not change results).')
     return parser
 
 
@@ -107,6 +110,14 @@ def _load_inputs(args, project_folder):
         with open(args.network_file, 'rb') as fh:
             graph = pickle.load(fh)
         return genes, graph
+    if args.network_source == 'sif_full' and args.id_type == 'custom' and not args.genes.endswith('.pkl'):
+        # a complete user network with custom ids needs nothing from the reference's resource
+        # layer: read it straight into CSR arrays (edgelist.py; nx_mg_assembler.py:368-422)
+        from .edgelist import read_network
+        with open(args.genes) as fh:
+            ids = [ln.strip() for ln in fh if ln.strip()]
+        genes = [{'ID': g} for g in dict.fromkeys(ids)]
+        return genes, read_network(args.network_file, 'sif_full', genes, obo=args.go_obo)
     try:
         from genewalk.gene_lists import read_gene_list
         from genewalk.nx_mg_assembler import load_network
@@ -148,8 +159,10 @@ def run_main(args):
         if args.stage in ('all', 'node_vectors'):
             genes, graph = _load_inputs(args, project_folder)
             save_pickle(genes, project_folder, 'genes')
-            save_pickle(graph, project_folder, 'multi_graph')
-            # cli.py:200-214; the replicates are independent and trained `--concurrent` at a time
+            # multi_graph.pkl always holds an nx.MultiGraph, as the reference writes it
+            save_pickle(graph.to_networkx() if hasattr(graph, 'to_networkx') else graph,
+                        project_folder, 'multi_graph')
+            # cli.py:200-214; the replicates are independent: up to `--concurrent` are in flight at a time
             step = max(1, args.concurrent)
             for i0 in range(0, args.nreps_graph, step):
                 cnt = min(step, args.nreps_graph - i0)

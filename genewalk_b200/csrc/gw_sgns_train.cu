@@ -59,10 +59,14 @@ struct TrainParams {
     uint32_t key0, key1;
 };
 
-// gw_sgns_auto_shape: see DESIGN.md section 4.2 and profiles/parity_study_r02.md
-constexpr int64_t kAutoLanesMax = 1024;
-constexpr int64_t kAutoRowsPerLane = 8;
-constexpr int64_t kAutoUnitWalks = 1000;
+// gw_sgns_auto_shape (profiles/parity_study_r02.md): workers ~ n/24, units of
+// ~0.36 n^0.75 consecutive walks.  Empirical: the shapes that score best against the sequential
+// oracle on the 2.3k-, 8.5k- and 38k-node study networks (95 x 120, 354 x 320, 1536 x 980).
+constexpr int64_t kAutoLanesMax = 1536;
+constexpr int64_t kAutoLanesMin = 16;
+constexpr int64_t kAutoRowsPerLane = 24;
+constexpr int64_t kAutoUnitMin = 50;
+constexpr int64_t kAutoUnitMax = 1000;
 constexpr int32_t kAutoPolicy = GW_PLAN_CHUNK;
 
 // ---- per-lane slice of a row: E consecutive floats ---------------------------------------------
@@ -731,16 +735,31 @@ extern "C" int gw_sgns_auto_shape(int32_t n, int64_t W, int64_t job_walks, int64
     using namespace gw;
     GW_REQUIRE(n > 0 && W > 0 && job_walks > 0 && lanes_out && unit_walks_out && policy_out,
                "gw_sgns_auto_shape: bad arguments");
-    int64_t lanes = kAutoLanesMax;
-    if (lanes > n / kAutoRowsPerLane) lanes = n / kAutoRowsPerLane;
-    if (lanes < 1) lanes = 1;
-    const int64_t unit = kAutoUnitWalks;
+    int64_t lanes = n / kAutoRowsPerLane;
+    if (lanes > kAutoLanesMax) lanes = kAutoLanesMax;
+    if (lanes < kAutoLanesMin) lanes = kAutoLanesMin;
+    if (lanes > n / 2) lanes = n / 2 > 0 ? n / 2 : 1;
+    int64_t unit = (int64_t)(0.36 * pow((double)n, 0.75) + 0.5);
+    if (unit > kAutoUnitMax) unit = kAutoUnitMax;
+    if (unit < kAutoUnitMin) unit = kAutoUnitMin;
+    if (unit > W) unit = W;
     const int64_t nunits = ceil_div<int64_t>(W, unit);
     if (lanes > nunits) lanes = nunits;
     *lanes_out = lanes;
     *unit_walks_out = unit;
     *policy_out = kAutoPolicy;
     return GW_OK;
+}
+
+extern "C" int gw_sgns_resident_trainings(int32_t d, int64_t lanes)
+{
+    using namespace gw;
+    if (lanes < 1) lanes = 1;
+    const int G = d / 2 > 32 ? 32 : (d / 2 < 1 ? 1 : d / 2);
+    // the kernels need <= 128 registers per thread: 512 threads (4 CTAs of 128) per SM
+    const int64_t threads = (int64_t)num_sms() * 512;
+    const int64_t fit = threads / (lanes * G);
+    return (int)(fit < 1 ? 1 : fit > 1024 ? 1024 : fit);
 }
 
 extern "C" int gw_sgns_train(int32_t n, int32_t d, const int32_t *tokens, const int32_t *row_ptr,
@@ -768,6 +787,10 @@ extern "C" int gw_sgns_train(int32_t n, int32_t d, const int32_t *tokens, const 
     }
     if (d != 8 && d != 16 && d != 32 && d != 64 && d != 128) {
         set_error("gw_sgns_train: vector_size=%d is not implemented (8, 16, 32, 64, 128)", d);
+        return GW_ERR_UNSUPPORTED;
+    }
+    if ((flags & GW_SGNS_MERGED) && K != 5) {
+        set_error("gw_sgns_train: GW_SGNS_MERGED is implemented for negative=5 only (got %d)", K);
         return GW_ERR_UNSUPPORTED;
     }
     GW_REQUIRE((reinterpret_cast<uintptr_t>(syn0) & 15) == 0 && (reinterpret_cast<uintptr_t>(syn1neg) & 15) == 0 &&

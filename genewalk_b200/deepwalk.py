@@ -265,8 +265,8 @@ class DeepWalk(object):
         the units the workers take from the queue, see ``gw_sgns_plan``; 0 / None = library
         default), ``reductions`` ('per_pair' | 'merged': see ``gw_sgns_flags`` in
         include/genewalk_b200.h), ``wait`` (False: only enqueue the training on the current CUDA
-        stream; ``finish_word2vec()`` then downloads the vectors) and ``sgns_seed`` (Philox key of
-        the negative draws).
+        stream; ``finish_word2vec()`` then downloads the vectors), ``sgns_seed`` (Philox key of
+        the negative draws) and ``epoch_hook`` (see ``train_device``).
         """
         import torch
         _lib.require_cuda()
@@ -283,6 +283,7 @@ class DeepWalk(object):
         reductions = kwargs.pop('reductions', 'per_pair')
         kwargs_async = not bool(kwargs.pop('wait', True))
         sgns_seed = kwargs.pop('sgns_seed', None)
+        epoch_hook = kwargs.pop('epoch_hook', None)
         if kwargs:
             raise TypeError('word2vec() got unexpected keyword arguments %s' % sorted(kwargs))
         if sg != 1:
@@ -305,7 +306,8 @@ class DeepWalk(object):
                                           alpha=alpha, min_alpha=min_alpha, init_seed=init_seed,
                                           ns_exponent=ns_exponent, batch_words=batch_words,
                                           lanes=lanes, unit_walks=unit_walks, policy=policy,
-                                          reductions=reductions, sgns_seed=sgns_seed)
+                                          reductions=reductions, sgns_seed=sgns_seed,
+                                          epoch_hook=epoch_hook)
         if kwargs_async:
             return          # training is enqueued; finish_word2vec() downloads the vectors
         self.finish_word2vec()
@@ -320,12 +322,14 @@ class DeepWalk(object):
         self._pending = None
         self.train_shape = {k: dv[k] for k in ('lanes', 'unit_walks', 'policy', 'regenerated')}
         nodes = dv['nodes']
+        # plain device-to-host copies and host-side gathers: no torch kernel is launched here, so
+        # nothing can trigger a lazy kernel load (which waits for an idle device) while other
+        # replicates are training on their streams
         nv = int(dv['n_vocab'].item())
-        order = dv['node_of_rank'][:nv].long()
-        vectors = dv['syn0'].index_select(0, order).cpu().numpy()
-        out_layer = dv['syn1neg'].index_select(0, order).cpu().numpy()
-        cnt = dv['counts'].index_select(0, order).cpu().numpy()
-        order_h = order.cpu().numpy()
+        order_h = dv['node_of_rank'].cpu().numpy()[:nv].astype(np.int64)
+        vectors = dv['syn0'].cpu().numpy()[order_h]
+        out_layer = dv['syn1neg'].cpu().numpy()[order_h]
+        cnt = dv['counts'].cpu().numpy()[order_h]
         wv = NodeVectors([nodes[i] for i in order_h], vectors, counts=cnt)
         wv.node_ids = order_h.astype(np.int32)   # row r of wv.vectors is graph node node_ids[r]
         self.model = Word2VecModel(wv, syn1neg=out_layer, corpus_count=dv['W'], **self._w2v_args)
@@ -335,9 +339,9 @@ class DeepWalk(object):
                      init_seed=1, ns_exponent=0.75, batch_words=10000, lanes=0, unit_walks=0,
                      policy=None, reductions='per_pair', sgns_seed=None, epoch_hook=None):
         """Enqueue vocabulary, alias table, init and the SGNS epochs on the current stream and
-        return the device tensors (no host synchronisation).  ``epoch_hook(ep, when)`` is called
-        with when in {'before', 'after'} around every epoch's launch (bench.py records CUDA
-        events there)."""
+        return the device tensors (no host synchronisation).  ``epoch_hook(stage, when)`` is called
+        with when in {'before', 'after'} around the vocabulary pass (stage 'count') and around every
+        epoch's launch (stage = epoch number); bench.py records CUDA events there."""
         import ctypes
         import torch
         nodes, n, tokens, wc = self._device_corpus()
@@ -362,11 +366,15 @@ class DeepWalk(object):
         # generator fills row-major, so the first V rows of an (n, d) draw are the (V, d) draw
         rng_rows = _init_rows(n, d, init_seed, dev)
         graph = wc.csr.to_device() if wc is not None else None
+        if epoch_hook is not None:
+            epoch_hook('count', 'before')
         if tokens is not None:
             _lib.call('gw_count_tokens', _lib.ptr(tokens), L * W, n, _lib.ptr(counts), st)
         else:
             _lib.call('gw_walk_count', n, graph.nnz, _lib.ptr(graph.d_row_ptr), _lib.ptr(graph.d_col_idx),
                       wc.niter, L, wc.seed, _lib.ptr(counts), st)
+        if epoch_hook is not None:
+            epoch_hook('count', 'after')
         _lib.call('gw_vocab_rank', n, _lib.ptr(counts), _lib.ptr(rank_of_node),
                   _lib.ptr(node_of_rank), _lib.ptr(n_vocab), st)
         _lib.call('gw_alias_build', n, _lib.ptr(counts), float(ns_exponent), _lib.ptr(alias), st)

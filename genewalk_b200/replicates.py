@@ -16,7 +16,7 @@ import numpy as np
 
 from . import _lib
 from .csr import GraphCSR, multigraph_degrees
-from .deepwalk import DeepWalk
+from .deepwalk import DeepWalk, _csr_of
 from .null_distributions import get_rand_graph
 from .perform_statistics import GeneWalk
 
@@ -41,7 +41,10 @@ def mix_seed(base_seed, stream, rep):
 def plan_units(nreps_graph, nreps_null, world_size=1, rank=0):
     """Units of this rank: [(kind, rep)], round-robin over real replicates then null replicates."""
     units = [(KIND_REAL, r) for r in range(nreps_graph)] + [(KIND_NULL, r) for r in range(nreps_null)]
-    return [u for i, u in enumerate(units) if i % world_size == rank]
+    mine = [u for i, u in enumerate(units) if i % world_size == rank]
+    # longest first: a randomized network has ~1.3x the adjacency entries (hence walks) of the real
+    # one, so its replicates are started first and the shorter ones fill the tail
+    return sorted(mine, key=lambda u: (-u[0], u[1]))
 
 
 def owner_of(kind, rep, nreps_graph, world_size):
@@ -131,19 +134,29 @@ def exchange_results(local_sims, local_null, nreps_graph, nreps_null, m, device,
 # ---------------------------------------------------------------------------------------------
 # the replicate bodies
 # ---------------------------------------------------------------------------------------------
-DEFAULT_CONCURRENT = 24   # replicates in flight per GPU: all units of an nreps = 10 + 10 run
+DEFAULT_CONCURRENT = 24   # upper bound of the replicates in flight per GPU
 
 
-def fit_concurrent(requested, n, vector_size=8):
-    """Replicates to run at once: ``requested``, capped by the free HBM.  The walks are never stored
-    (the trainer regenerates them), so a replicate in flight holds only its tables, vocabulary,
-    noise table, unit plan and (null replicates) its randomized graph: a few MB at human scale.
-    The number in flight does NOT change any replicate's result: every training gets the same
-    number of workers whatever shares the GPU with it (gw_sgns_auto_shape)."""
+def fit_concurrent(requested, n, vector_size=8, walks=None, lanes=0):
+    """Replicates to keep in flight at once: at most ``requested``, at most as many trainings as
+    are RESIDENT on the GPU together with the workers each of them gets (``lanes``, default: the
+    library's shape for an ``n``-node network) -- so that every training really runs with its full
+    set of workers, whatever else shares the GPU, and a replicate's result does not depend on how
+    many replicates run next to it -- and capped by the free HBM.  The walks are never stored (the
+    trainer regenerates them), so a replicate in flight holds only its tables, vocabulary, noise
+    table, unit plan and (null replicates) its randomized graph: a few MB at human scale."""
+    import ctypes
     import torch
+    lib = _lib.load()
+    if not lanes:
+        a_l, a_u, a_p = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int32(0)
+        _lib.call('gw_sgns_auto_shape', int(n), int(walks) if walks else 100 * int(n), 1000,
+                  ctypes.byref(a_l), ctypes.byref(a_u), ctypes.byref(a_p))
+        lanes = a_l.value
+    resident = int(lib.gw_sgns_resident_trainings(int(vector_size), int(lanes)))
     per_replicate = int(n) * (2 * 4 * int(vector_size) + 64) + (64 << 20)
     free, _ = torch.cuda.mem_get_info()
-    return max(1, min(int(requested), int(0.8 * free) // per_replicate))
+    return max(1, min(int(requested), resident, int(0.8 * free) // per_replicate))
 
 
 def real_replicate(csr, base_seed, rep, dim_rep=8, walk_length=10, niter=100, wait=True, **w2v):
@@ -240,13 +253,21 @@ def preload_kernels(dim_rep=8, **w2v):
     _PRELOADED.add(key)
 
 
+def _new_event(timing=False):
+    import torch
+    return torch.cuda.Event(enable_timing=timing)
+
+
 def _run_rolling(n_units, nstreams, enqueue, finish, timeline=None):
-    """Keeps up to ``nstreams`` units in flight, unit i on CUDA stream i % nstreams: before unit i is
-    enqueued, unit i - nstreams (the previous one on that stream) is finished, so there is no
-    barrier between rounds -- the other streams keep the GPU busy meanwhile -- and at most
-    ``nstreams`` replicates are alive.  ``enqueue(i)`` and ``finish(i, job)`` run with the unit's stream current.  Units are finished in
-    order.  ``timeline`` (a list) receives ``(unit, stream, begin_ms, end_ms)`` of the device work
-    enqueued by ``enqueue``, measured with CUDA events relative to the first unit's begin."""
+    """Keeps up to ``nstreams`` units in flight, one per CUDA stream: whenever the unit of a stream
+    has completed on the device (polled with CUDA events, so the host never blocks on one stream
+    while another has gone idle), it is finished and the next unit -- units are handed out in
+    order 0, 1, 2, ... -- is enqueued on that stream.  There is no barrier between rounds and at
+    most ``nstreams`` replicates are alive.  ``enqueue(i)`` and ``finish(i, job)`` run with the
+    unit's stream current.  ``timeline`` (a list) receives ``(unit, stream, begin_ms, end_ms)`` of
+    the device work enqueued by ``enqueue``, measured with CUDA events relative to the first
+    unit's begin."""
+    import time
     import torch
     cur = torch.cuda.current_stream()
     nstreams = max(1, min(int(nstreams), n_units))
@@ -254,25 +275,38 @@ def _run_rolling(n_units, nstreams, enqueue, finish, timeline=None):
     for st in streams:
         if st is not cur:
             st.wait_stream(cur)
-    inflight = [None] * nstreams
+    inflight = {}
     events = []
-    for i in range(n_units):
-        k = i % nstreams
+    next_unit = 0
+
+    def start(k):
+        nonlocal next_unit
+        i = next_unit
+        next_unit += 1
         with torch.cuda.stream(streams[k]):
-            if inflight[k] is not None:
-                finish(*inflight[k])
-            if timeline is not None:
-                e0 = torch.cuda.Event(enable_timing=True)
+            e0 = _new_event(True) if timeline is not None else None
+            if e0 is not None:
                 e0.record()
-            inflight[k] = (i, enqueue(i))
+            job = enqueue(i)
+            e1 = _new_event(timeline is not None)
+            e1.record()
             if timeline is not None:
-                e1 = torch.cuda.Event(enable_timing=True)
-                e1.record()
                 events.append((i, k, e0, e1))
-    for k in sorted((k for k in range(nstreams) if inflight[k] is not None),
-                    key=lambda k: inflight[k][0]):
-        with torch.cuda.stream(streams[k]):
-            finish(*inflight[k])
+        inflight[k] = (i, job, e1)
+
+    for k in range(nstreams):
+        start(k)
+    while inflight:
+        ready = [k for k in sorted(inflight, key=lambda k: inflight[k][0]) if inflight[k][2].query()]
+        if not ready:
+            time.sleep(0.0005)
+            continue
+        for k in ready:
+            i, job, _ = inflight.pop(k)
+            with torch.cuda.stream(streams[k]):
+                finish(i, job)
+            if next_unit < n_units:
+                start(k)
     for st in streams:
         if st is not cur:
             cur.wait_stream(st)
@@ -291,7 +325,7 @@ def run_walks_many(graph, n_replicates, base_seed=None, concurrent=DEFAULT_CONCU
     _lib.require_cuda()
     if base_seed is None:
         base_seed = random.getrandbits(64)
-    csr = GraphCSR.from_networkx(graph).to_device() if not isinstance(graph, GraphCSR) else graph.to_device()
+    csr = _csr_of(graph).to_device()
     out = []
 
     def enqueue(rep):
@@ -300,7 +334,7 @@ def run_walks_many(graph, n_replicates, base_seed=None, concurrent=DEFAULT_CONCU
     def finish(rep, dw):
         dw.finish_word2vec()
         out.append(dw)
-    nstreams = fit_concurrent(concurrent, csr.n, vector_size)
+    nstreams = fit_concurrent(concurrent, csr.n, vector_size, niter * csr.nnz, w2v.get('lanes', 0))
     if min(nstreams, n_replicates) > 1:
         preload_kernels(vector_size, **w2v)
     _run_rolling(n_replicates, nstreams, enqueue, finish)
@@ -322,7 +356,8 @@ def null_replicates_many(mg, n_replicates, base_seed=None, concurrent=DEFAULT_CO
     def finish(rep, job):
         out.append((job.dw, job.finish(keep_model=keep_model).cpu().numpy()))
     degrees = multigraph_degrees(mg)
-    nstreams = fit_concurrent(concurrent, len(degrees), vector_size)
+    nstreams = fit_concurrent(concurrent, len(degrees), vector_size, niter * int(degrees.sum()),
+                              w2v.get('lanes', 0))
     if min(nstreams, n_replicates) > 1:
         preload_kernels(vector_size, **w2v)
     _run_rolling(n_replicates, nstreams, enqueue, finish)
@@ -331,15 +366,17 @@ def null_replicates_many(mg, n_replicates, base_seed=None, concurrent=DEFAULT_CO
 
 def run_genewalk(mg, genes, nreps_graph=3, nreps_null=3, alpha_fdr=1, gene_id_type='hgnc_symbol',
                  dim_rep=8, base_seed=None, group=None, return_parts=False,
-                 concurrent=DEFAULT_CONCURRENT, **w2v):
+                 concurrent=DEFAULT_CONCURRENT, shard=True, walk_length=10, niter=100, **w2v):
     """node_vectors + null_distribution + statistics stages of cli.run_main (cli.py:194-252) for an
     assembled ``nx.MultiGraph``; replicates are sharded over the ranks of the initialised process
     group (one process per GPU) and, on every GPU, up to ``concurrent`` of them are trained at once
-    on separate CUDA streams.  Returns the results DataFrame (identical on every rank)."""
+    on separate CUDA streams.  ``shard=False`` runs every replicate on the calling rank and uses no
+    collective (independent runs on the GPUs of a node).  Returns the results DataFrame (identical
+    on every rank)."""
     import time
     import torch
     _lib.require_cuda()
-    ws, rank = world()
+    ws, rank = world() if shard else (1, 0)
     t_start = time.perf_counter()
     if base_seed is None:
         base_seed = random.getrandbits(64)
@@ -347,11 +384,12 @@ def run_genewalk(mg, genes, nreps_graph=3, nreps_null=3, alpha_fdr=1, gene_id_ty
             t = torch.tensor([base_seed & (2 ** 63 - 1)], dtype=torch.int64, device='cuda')
             _dist().broadcast(t, 0, group=group)
             base_seed = int(t.item())
-    csr = GraphCSR.from_networkx(mg).to_device()
+    csr = _csr_of(mg).to_device()
     gw = GeneWalk(mg, genes, [], np.zeros(1, np.float32), gene_id_type=gene_id_type)
     pairs = gw.collect_pairs()
     m = len(pairs['pair_go'])
     local_sims, local_null, nvs = {}, {}, {}
+    walks_trained, shapes = [], []
     units = plan_units(nreps_graph, nreps_null, ws, rank)
     degrees = multigraph_degrees(mg) if any(k == KIND_NULL for k, _ in units) else None
     t_setup = time.perf_counter()
@@ -363,7 +401,7 @@ def run_genewalk(mg, genes, nreps_graph=3, nreps_null=3, alpha_fdr=1, gene_id_ty
         kind, rep = units[i]
         if kind == KIND_REAL:
             logger.info('real replicate %d/%d on rank %d' % (rep + 1, nreps_graph, rank))
-            dw = real_replicate(csr, base_seed, rep, dim_rep, wait=False, **w2v)
+            dw = real_replicate(csr, base_seed, rep, dim_rep, walk_length, niter, wait=False, **w2v)
             # gene-GO similarities straight from the device table (rows are graph node ids, the
             # index space of `pairs`; every node of a pair has an edge, hence walks, hence a row):
             # perform_statistics.py:102 without the round trip through host vectors
@@ -372,9 +410,15 @@ def run_genewalk(mg, genes, nreps_graph=3, nreps_null=3, alpha_fdr=1, gene_id_ty
                 _lib.call('gw_cosine_pairs', int(dim_rep), _lib.ptr(dw._pending['syn0']), m,
                           _lib.ptr(d_pg), _lib.ptr(d_po), _lib.ptr(sims), _lib.stream_ptr())
             local_sims[rep] = sims
+            walks_trained.append(dw._pending['W'])
+            shapes.append((dw._pending['lanes'], dw._pending['unit_walks'], dw._pending['policy']))
             return dw
         logger.info('null replicate %d/%d on rank %d' % (rep + 1, nreps_null, rank))
-        return _NullJob(mg, base_seed, rep, dim_rep, 10, 100, dict(w2v), degrees=degrees)
+        job = _NullJob(mg, base_seed, rep, dim_rep, walk_length, niter, dict(w2v), degrees=degrees)
+        walks_trained.append(len(job.dw.walks))
+        if job.dw._pending is not None:
+            shapes.append((job.dw._pending['lanes'], job.dw._pending['unit_walks'], job.dw._pending['policy']))
+        return job
 
     def finish(i, job):
         kind, rep = units[i]
@@ -386,14 +430,19 @@ def run_genewalk(mg, genes, nreps_graph=3, nreps_null=3, alpha_fdr=1, gene_id_ty
         else:
             local_null[rep] = job.finish()
     timeline = [] if return_parts else None
-    nstreams = fit_concurrent(concurrent, csr.n, dim_rep)
+    nstreams = fit_concurrent(concurrent, csr.n, dim_rep, niter * csr.nnz, w2v.get('lanes', 0))
     if min(nstreams, len(units)) > 1:
         preload_kernels(dim_rep, **w2v)
     _run_rolling(len(units), nstreams, enqueue, finish, timeline)
     torch.cuda.synchronize()
     t_units = time.perf_counter()
     dev = torch.device('cuda')
-    sims, nulls = exchange_results(local_sims, local_null, nreps_graph, nreps_null, m, dev, group)
+    if ws > 1:
+        sims, nulls = exchange_results(local_sims, local_null, nreps_graph, nreps_null, m, dev, group)
+    else:
+        sims = torch.stack([local_sims[r] for r in range(nreps_graph)]) if nreps_graph else \
+            torch.zeros((0, m), dtype=torch.float32, device=dev)
+        nulls = [local_null[r] for r in range(nreps_null)]
     pooled = torch.cat(nulls) if nulls else torch.zeros(0, dtype=torch.float32, device=dev)
     if pooled.numel() > 0:   # cli.py:238: srd = np.asarray(sorted(srd))
         pooled = pooled.contiguous()
@@ -409,6 +458,6 @@ def run_genewalk(mg, genes, nreps_graph=3, nreps_null=3, alpha_fdr=1, gene_id_ty
     logger.info('run_genewalk timings: %s' % timings)
     if return_parts:
         return df, {'sims': sims, 'null': gw.srd, 'nvs': nvs, 'base_seed': base_seed,
-                    'timings': timings,
+                    'timings': timings, 'walks_trained_local': int(sum(walks_trained)), 'train_shapes_local': shapes,
                     'timeline': [(units[i], k, b, e) for i, k, b, e in timeline]}
     return df

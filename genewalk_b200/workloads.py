@@ -173,3 +173,34 @@ def csr_from_edges_numpy(n, u, v):
     row_ptr = np.zeros(n + 1, dtype=np.int64)
     np.add.at(row_ptr, src + 1, 1)
     return np.cumsum(row_ptr).astype(np.int32), dst
+
+
+def indra_scale_edges(seed=3, n=50000, m=5000000):
+    """C4 (BASELINE.json configs[3]): INDRA-scale dense multigraph -- 50k nodes, 5M multi-edges drawn
+    from a Chung-Lu model with Pareto(1.8) weights, so many pairs repeat (they collapse to ~10M
+    adjacency entries) and the largest degrees reach ~1e4.  Returns (n, u, v)."""
+    rng = np.random.default_rng(seed)
+    w = rng.pareto(1.8, size=n) + 1.0
+    w /= w.sum()
+    u = rng.choice(n, size=m, p=w).astype(np.int32)
+    v = rng.choice(n, size=m, p=w).astype(np.int32)
+    keep = u != v
+    return n, u[keep], v[keep]
+
+
+def power_law_stress_edges(seed=4, n=1000000, m=5000000):
+    """C5 (BASELINE.json configs[4]): 1M-node power-law graph (Barabasi-Albert-like, m = 5:
+    ~10M adjacency entries), no GO attributes.  Returns (n, u, v)."""
+    rng = np.random.default_rng(seed)
+    w = (np.arange(1, n + 1, dtype=np.float64)) ** -0.5
+    w /= w.sum()
+    u = rng.choice(n, size=m, p=w).astype(np.int32)
+    v = rng.choice(n, size=m, p=w).astype(np.int32)
+    keep = u != v
+    return n, u[keep], v[keep]
+
+
+def multigraph_degrees_from_edges(n, u, v):
+    """``mg.degree`` of the multigraph with edges (u[k], v[k]): parallel edges counted, a
+    self-loop counts 2."""
+    return (np.bincount(u, minlength=n) + np.bincount(v, minlength=n)).astype(np.int64)

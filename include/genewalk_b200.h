@@ -171,7 +171,8 @@ int gw_sgns_plan(int32_t n, const int32_t *row_ptr, int32_t niter, int64_t W, in
  *     inside a step, and the two updates of syn0[walk[j]] from steps j-1 and j+1, are summed in
  *     registers and reduced once; rows are still read from the table right before use and the
  *     worker adds its own held-back update, so its arithmetic sees every one of its updates.
- *     Both orders are bit-exact against the oracle when run with lanes == 1. */
+ *     Both orders are bit-exact against the oracle when run with lanes == 1.  MERGED is
+ *     implemented for K == 5 (GeneWalk's setting); other K return GW_ERR_UNSUPPORTED with it. */
 enum gw_sgns_flags { GW_SGNS_MERGED = 4 };
 int gw_sgns_train(int32_t n, int32_t d, const int32_t *tokens, const int32_t *row_ptr,
                   const int32_t *col_idx, int32_t niter, uint64_t walk_seed, int64_t W, int32_t L,
@@ -186,6 +187,11 @@ int gw_sgns_train(int32_t n, int32_t d, const int32_t *tokens, const int32_t *ro
  * replicates are spread over, so a seed gives the same statistics at every GPU count. */
 int gw_sgns_auto_shape(int32_t n, int64_t W, int64_t job_walks, int64_t *lanes_out,
                        int64_t *unit_walks_out, int32_t *policy_out);
+
+/* How many trainings of `lanes` workers (vector size d) are resident on the current device at
+ * once: the replicate driver keeps at most that many in flight, so that every training really runs
+ * with the workers it was given whatever else shares the GPU. */
+int gw_sgns_resident_trainings(int32_t d, int64_t lanes);
 
 /* ---- (4) similarity statistics ------------------------------------------------------------ */
 

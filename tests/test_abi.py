@@ -55,7 +55,8 @@ def test_ctypes_table_matches_header_arity():
             name, len(argtypes), len(fns[name]))
     for name, argtypes in _lib.INT64_RETURNS.items():
         assert len(argtypes) == len(fns[name])
-    bound = set(_lib.SIGNATURES) | set(_lib.INT64_RETURNS) | {'gw_last_error', 'gw_launch_count'}
+    bound = set(_lib.SIGNATURES) | set(_lib.INT64_RETURNS) | set(_lib.INT_RETURNS) | \
+        {'gw_last_error', 'gw_launch_count'}
     assert set(fns) == bound
 
 

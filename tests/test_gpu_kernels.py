@@ -327,7 +327,7 @@ def test_sgns_regenerated_walks_bit_exact(n, m, niter, L, d, K, epochs):
     counts = np.bincount(tok.ravel(), minlength=n)
     prob, alias = olib.alias_table(counts)
     syn0, syn1 = olib.gensim_init_weights(n, d, seed=1)
-    for merged in (False, True):
+    for merged in ((False, True) if K == 5 else (False,)):
         want0, want1 = syn0.copy(), syn1.copy()
         olib.sgns_train(tok, n, d, want0, want1, sampler=1, K=K, epochs=epochs, job_walks=50,
                         alias_prob=prob, alias_idx=alias, seed=5, merged=merged)
@@ -451,9 +451,11 @@ def test_sgns_ragged_walks_bit_exact():
 
 def test_sgns_unsupported_raises():
     tok, prob, alias, syn0, syn1 = sgns_case(20, 50, 1, 5, 8, 5, 1, seed=1)
+    with pytest.raises(NotImplementedError):      # merged order exists for negative=5 only
+        gpu_sgns(tok, 20, 8, 3, 1, prob, alias, syn0, syn1, 1, lanes=1, flags=4)
     with pytest.raises(NotImplementedError):
         gpu_sgns(tok, 20, 12, 5, 1, prob, alias, np.zeros((20, 12), np.float32),
-                 np.zeros((20, 12), np.float32), 1, 0)
+                 np.zeros((20, 12), np.float32), 1, lanes=1)
 
 
 def test_sgns_hogwild_close_to_sequential():
@@ -486,6 +488,9 @@ def test_sgns_auto_shape():
         assert lanes.value * unit.value <= max(W, unit.value)
         seen.append(lanes.value)
     assert seen[0] <= seen[1] <= seen[2]
+    lib = _lib.load()
+    assert lib.gw_sgns_resident_trainings(8, 1536) == 148 * 128 // 1536
+    assert lib.gw_sgns_resident_trainings(8, 1) >= 1024 and lib.gw_sgns_resident_trainings(128, 10 ** 6) == 1
 
 
 # ------------------------------------------------------------------------------------------------

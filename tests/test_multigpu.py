@@ -27,3 +27,8 @@ def test_two_gpu_pipeline(tmp_path):
     assert np.array_equal(r0['null'], r1['null']) and np.all(np.diff(r0['null']) >= 0)
     assert np.array_equal(r0['padj'], r1['padj'], equal_nan=True)
     assert np.isfinite(r0['sims']).all() and len(r0['null']) > 3 * 3000
+    # sequential SGNS mode: the 2-GPU run equals the 1-GPU run bit for bit
+    assert bool(r0['seq_equal']) and bool(r1['seq_equal'])
+    # default mode: every training has the same shape (workers, unit) on 1 and on 2 GPUs
+    shapes = {tuple(x) for r in (r0, r1) for k in ('shapes_sharded', 'shapes_unsharded') for x in r[k]}
+    assert len(shapes) == 1, shapes

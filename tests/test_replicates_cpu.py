@@ -88,10 +88,11 @@ def test_exchange_over_gloo_world_size_2(ng, nn):
     assert list(out) == [1] * ws
 
 
-def test_rolling_schedule_order_and_shares(monkeypatch):
-    """_run_rolling: unit i runs on stream i % nstreams, unit i - nstreams is finished right before
-    unit i is enqueued (no barrier between rounds), units finish in order, and the last, smaller
-    round is told how many units share the GPU.  CUDA streams are replaced by dummies."""
+def test_rolling_schedule_order(monkeypatch):
+    """_run_rolling: at most nstreams units in flight, one per stream; a stream whose unit has
+    completed on the device gets the next unit (no barrier between rounds, no waiting on a busy
+    stream while another is idle).  CUDA streams and events are replaced by dummies; a fake clock
+    decides which units are complete."""
     import contextlib
     import torch
     from genewalk_b200 import replicates as R
@@ -105,6 +106,18 @@ def test_rolling_schedule_order_and_shares(monkeypatch):
     cur = FakeStream('cur')
     side = [FakeStream('s%d' % k) for k in range(8)]
     active = []
+    done = set()
+
+    class FakeEvent(object):
+        unit = None
+
+        def record(self):
+            self.unit = current_unit[0]
+
+        def query(self):
+            return self.unit in done
+
+    current_unit = [None]
 
     @contextlib.contextmanager
     def fake_ctx(stream):
@@ -114,43 +127,72 @@ def test_rolling_schedule_order_and_shares(monkeypatch):
     monkeypatch.setattr(torch.cuda, 'current_stream', lambda: cur)
     monkeypatch.setattr(torch.cuda, 'stream', fake_ctx)
     monkeypatch.setattr(R, '_side_streams', lambda count: side[:count])
+    monkeypatch.setattr(R, '_new_event', lambda timing=False: FakeEvent())
     log = []
-    R._run_rolling(8, 3, lambda i: log.append(('enq', i, active[-1])) or ('job', i),
-                   lambda i, job: log.append(('fin', i, job, active[-1])))
+    # unit durations: unit 1 is slow, so stream s1 is skipped over while s0 and s2 take new units
+    finish_order = iter([0, 2, 3, 4, 1, 5, 6, 7])
+
+    def enqueue(i):
+        current_unit[0] = i
+        log.append(('enq', i, active[-1]))
+        return ('job', i)
+
+    def fake_sleep(dt):
+        done.add(next(finish_order))
+    import time
+    monkeypatch.setattr(time, 'sleep', fake_sleep)
+    R._run_rolling(8, 3, enqueue, lambda i, job: log.append(('fin', i, job, active[-1])))
     want = [('enq', 0, 's0'), ('enq', 1, 's1'), ('enq', 2, 's2'),
             ('fin', 0, ('job', 0), 's0'), ('enq', 3, 's0'),
-            ('fin', 1, ('job', 1), 's1'), ('enq', 4, 's1'),
-            ('fin', 2, ('job', 2), 's2'), ('enq', 5, 's2'),
-            ('fin', 3, ('job', 3), 's0'), ('enq', 6, 's0'),
-            ('fin', 4, ('job', 4), 's1'), ('enq', 7, 's1'),
-            ('fin', 5, ('job', 5), 's2'), ('fin', 6, ('job', 6), 's0'), ('fin', 7, ('job', 7), 's1')]
+            ('fin', 2, ('job', 2), 's2'), ('enq', 4, 's2'),
+            ('fin', 3, ('job', 3), 's0'), ('enq', 5, 's0'),
+            ('fin', 4, ('job', 4), 's2'), ('enq', 6, 's2'),
+            ('fin', 1, ('job', 1), 's1'), ('enq', 7, 's1'),
+            ('fin', 5, ('job', 5), 's0'), ('fin', 6, ('job', 6), 's2'), ('fin', 7, ('job', 7), 's1')]
     assert log == want
     assert all(s.waited == ['cur'] for s in side[:3]) and cur.waited == ['s0', 's1', 's2']
     # a single stream degenerates to the serial loop on the current stream
     log.clear()
-    R._run_rolling(3, 1, lambda i: log.append(('enq', i, active[-1])) or i,
-                   lambda i, job: log.append(('fin', i, job, active[-1])))
-    assert log == [('enq', 0, 'cur'), ('fin', 0, 0, 'cur'), ('enq', 1, 'cur'),
-                   ('fin', 1, 1, 'cur'), ('enq', 2, 'cur'), ('fin', 2, 2, 'cur')]
+    done.clear()
+    finish_order = iter([0, 1, 2])
+    R._run_rolling(3, 1, enqueue, lambda i, job: log.append(('fin', i, job, active[-1])))
+    assert log == [('enq', 0, 'cur'), ('fin', 0, ('job', 0), 'cur'), ('enq', 1, 'cur'),
+                   ('fin', 1, ('job', 1), 'cur'), ('enq', 2, 'cur'), ('fin', 2, ('job', 2), 'cur')]
     # more streams than units
     log.clear()
-    R._run_rolling(2, 6, lambda i: log.append(('enq', i)) or i,
-                   lambda i, job: log.append(('fin', i)))
-    assert log == [('enq', 0), ('enq', 1), ('fin', 0), ('fin', 1)]
+    done.clear()
+    finish_order = iter([0, 1])
+    R._run_rolling(2, 6, enqueue, lambda i, job: log.append(('fin', i)))
+    assert log == [('enq', 0, 's0'), ('enq', 1, 's1'), ('fin', 0), ('fin', 1)]
 
 
-def test_fit_concurrent_caps_by_free_memory(monkeypatch):
-    """fit_concurrent: as many replicates in flight as asked for -- walks are never stored, a
-    replicate holds its tables, vocabulary and plan (64 MiB allowance + n * (8 d + 64) bytes) --
-    unless even that exceeds 80 % of the free HBM; never below one."""
+def test_fit_concurrent_caps_by_residency_and_memory(monkeypatch):
+    """fit_concurrent: as many replicates in flight as asked for, but never more trainings than are
+    resident on the GPU with their full worker count (so a replicate's result cannot depend on what
+    runs next to it), and never more than fit 80 % of the free HBM (walks are never stored: a
+    replicate holds its tables, vocabulary and plan, 64 MiB allowance + n * (8 d + 64) bytes)."""
     import torch
+    from genewalk_b200 import _lib
     from genewalk_b200 import replicates as R
+
+    class FakeLib(object):
+        @staticmethod
+        def gw_sgns_resident_trainings(d, lanes):
+            return max(1, 148 * 512 // (lanes * (d // 2)))
+    monkeypatch.setattr(_lib, 'load', lambda: FakeLib)
+
+    def fake_call(name, n, W, job, lanes, unit, policy):
+        assert name == 'gw_sgns_auto_shape'
+        lanes._obj.value = max(16, min(1536, n // 24))
+    monkeypatch.setattr(_lib, 'call', fake_call)
     state = {'free': 170 << 30}
     monkeypatch.setattr(torch.cuda, 'mem_get_info', lambda: (state['free'], 180 << 30))
-    assert R.fit_concurrent(24, 38000) == 24
-    assert R.fit_concurrent(24, 1000000, 128) == 24
+    assert R.fit_concurrent(24, 38000) == 148 * 128 // 1536          # 12 trainings of 1536 workers
+    assert R.fit_concurrent(24, 2300) == 24                            # 95 workers each: all fit
+    assert R.fit_concurrent(24, 38000, lanes=512) == 24
+    assert R.fit_concurrent(24, 1000000, 128) == 1                     # 1536 workers of 32 threads
     state['free'] = 1 << 30
-    assert R.fit_concurrent(24, 38000) == 11
+    assert R.fit_concurrent(24, 2300) == 12
     state['free'] = 1 << 20
-    assert R.fit_concurrent(24, 38000) == 1
+    assert R.fit_concurrent(24, 2300) == 1
     assert R.fit_concurrent(1, 10) == 1

@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <math.h>
+#include <string.h>
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1); } } while (0)
 __device__ __forceinline__ uint32_t lcg(uint32_t &s) { s = s * 1664525u + 1013904223u; return s; }
 
@@ -136,7 +137,11 @@ static void run(const char *name, float *table, const uint32_t *pick, uint32_t n
 
 int main(int argc, char **argv)
 {
-    const uint32_t n = 38000;
+    // --peak ROWS: only the uniform-row patterns over a table of ROWS rows (bench.py's live roofline
+    // denominator: the L2 sector-request rate of the step's gather + reduction mix without any
+    // same-row collisions to speak of)
+    const bool peak_only = argc > 2 && strcmp(argv[1], "--peak") == 0;
+    const uint32_t n = peak_only ? (uint32_t)strtoul(argv[2], nullptr, 10) : 38000;
     int sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
     float *table, *sink;
@@ -154,6 +159,13 @@ int main(int argc, char **argv)
     while (pos < np) { h[pos] = pos % n; ++pos; }
     for (uint32_t i = np - 1; i > 0; --i) { uint32_t j = (uint32_t)(((uint64_t)i * 2654435761u + 12345u) % (i + 1)); uint32_t t = h[i]; h[i] = h[j]; h[j] = t; }
     CK(cudaMalloc(&d_pl, np * 4)); CK(cudaMemcpy(d_pl, h, np * 4, cudaMemcpyHostToDevice));
+    if (peak_only) {
+        for (int per_sm = 128; per_sm <= 512; per_sm *= 2) {
+            run<13, 14>("uniform", table, d_uni, np, sms * per_sm / 64, 256, sink);
+            run<13, 0>("uniform", table, d_uni, np, sms * per_sm / 64, 256, sink);
+        }
+        return 0;
+    }
     if (argc > 1) {
         // row popularity of a real workload: a binary file of uint32 row ids drawn by the caller
         // (tools/make_pick.py: centre/context rows ~ degree, negatives ~ degree^0.75 of the C2 network)
