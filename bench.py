@@ -265,6 +265,8 @@ def run_ours(args):
     R_real, R_null = args.real, args.null
     R = R_real + R_null
     w2v = dict(lanes=args.lanes) if args.lanes else {}
+    if args.reductions != 'per_pair':
+        w2v['reductions'] = args.reductions
     preload_kernels(D, **w2v)
     in_flight = fit_concurrent(R, n, D, NITER * A, args.lanes)
     train_events, count_events = [], []
@@ -372,6 +374,8 @@ def run_ours(args):
     hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
     traffic, traffic_src = None, None
     try:
+        if args.config != 'c2' or args.scale != 1.0:
+            raise ValueError('the capture is of the c2 workload')
         with open(os.path.join(ROOT, 'profiles', 'r02_sgns_train_traffic.json')) as f:
             tj = json.load(f)
             traffic, traffic_src = tj.get('dram_bytes_per_launch'), tj.get('source')
@@ -457,8 +461,8 @@ def run_ours(args):
     if rank == 0:
         import ctypes
         a_l, a_u, a_p = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int32(0)
-        _lib.call('gw_sgns_auto_shape', n, NITER * A, 1000, ctypes.byref(a_l), ctypes.byref(a_u),
-                  ctypes.byref(a_p))
+        _lib.call('gw_sgns_auto_shape', n, NITER * A, 1000, NITER * int(csr.max_degree or 0),
+                  ctypes.byref(a_l), ctypes.byref(a_u), ctypes.byref(a_p))
         mix, gat, src = live_l2_peak(2 * R * n) if not args.no_l2_peak else (None, None, 'skipped')
         steps_per_s = walks_timed * PAIRS_PER_WALK / 2 / (busy_ms / 1e3)   # step = 2 pairs (13 gathers + 14 reductions)
         if mix is None:
@@ -549,13 +553,15 @@ def main():
                     help='c2: the headline workload (default); c4 / c5: BASELINE.json configs[3] / [4]')
     ap.add_argument('--scale', type=float, default=1.0, help='shrink the c2 workload (tests only)')
     ap.add_argument('--lanes', type=int, default=0, help='workers per training (0: library default)')
+    ap.add_argument('--reductions', default='per_pair', choices=['per_pair', 'merged'],
+                    help='reduction order of the trainer (library default: per_pair, gensim\'s order)')
     ap.add_argument('--real', type=int, default=None, help='real-network replicates per step')
     ap.add_argument('--null', type=int, default=None, help='randomized-network replicates per step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-pipeline', action='store_true')
     ap.add_argument('--no-l2-peak', action='store_true')
     args = ap.parse_args()
-    default_reps = {'c2': (10, 10), 'c4': (2, 2), 'c5': (2, 2)}[args.config]
+    default_reps = {'c2': (10, 10), 'c4': (6, 6), 'c5': (6, 6)}[args.config]
     if args.real is None:
         args.real = default_reps[0]
     if args.null is None:

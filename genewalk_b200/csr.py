@@ -28,6 +28,10 @@ class GraphCSR(object):
         self.d_row_ptr = None
         self.d_col_idx = None
         self._nnz = None if self.row_ptr is None else int(self.row_ptr[-1])
+        # largest number of distinct neighbours (or an upper bound of it), None = unknown: the
+        # trainer's default shape looks at the longest run of walks with one start node
+        self.max_degree = None if self.row_ptr is None or len(self.row_ptr) < 2 else \
+            int(np.diff(self.row_ptr).max())
 
     # -- construction ---------------------------------------------------------------------------
     @classmethod
@@ -46,11 +50,12 @@ class GraphCSR(object):
         return cls(nodes, row_ptr.astype(np.int32), col_idx, index)
 
     @classmethod
-    def from_device(cls, nodes, d_row_ptr, d_col_idx, nnz):
+    def from_device(cls, nodes, d_row_ptr, d_col_idx, nnz, max_degree=None):
         g = cls(nodes, None, None)
         g.d_row_ptr = d_row_ptr
         g.d_col_idx = d_col_idx
         g._nnz = int(nnz)
+        g.max_degree = None if max_degree is None else int(max_degree)
         return g
 
     # -- accessors --------------------------------------------------------------------------------

@@ -60,13 +60,20 @@ struct TrainParams {
 };
 
 // gw_sgns_auto_shape (profiles/parity_study_r02.md): workers ~ n/24, units of
-// ~0.36 n^0.75 consecutive walks.  Empirical: the shapes that score best against the sequential
-// oracle on the 2.3k-, 8.5k- and 38k-node study networks (95 x 120, 354 x 320, 1536 x 980).
+// ~0.36 n^0.75 consecutive walks, i.e. a window of walks in flight of 0.3-1 % of the corpus -- the
+// shapes that score best against the sequential oracle on the 2.3k-, 8.5k- and 38k-node study
+// networks (95 x 120, 354 x 320, 1536 x 980).  Networks with hubs (a start node owning >= 100k
+// walks) keep units of >= 320 walks: shorter units put every worker on the hub's walks at once and
+// its rows overshoot (max row norm 20-70 instead of 12-14).  Twice the workers with half the units
+// (the same window) train a lone replicate twice as fast and score the same KS, but were seen to
+// overshoot on a hub once in six runs (norm 55): not shipped.
 constexpr int64_t kAutoLanesMax = 1536;
 constexpr int64_t kAutoLanesMin = 16;
 constexpr int64_t kAutoRowsPerLane = 24;
 constexpr int64_t kAutoUnitMin = 50;
 constexpr int64_t kAutoUnitMax = 1000;
+constexpr int64_t kAutoHubWalks = 100000;
+constexpr int64_t kAutoHubUnitMin = 320;
 constexpr int32_t kAutoPolicy = GW_PLAN_CHUNK;
 
 // ---- per-lane slice of a row: E consecutive floats ---------------------------------------------
@@ -729,8 +736,8 @@ extern "C" int gw_sgns_plan(int32_t n, const int32_t *row_ptr, int32_t niter, in
 // Default parallel shape: a function of the network alone -- never of how
 // many trainings share the GPU or of how many GPUs the replicates are spread over, so that a seed
 // gives the same statistics on 1 and on 8 GPUs.
-extern "C" int gw_sgns_auto_shape(int32_t n, int64_t W, int64_t job_walks, int64_t *lanes_out,
-                                  int64_t *unit_walks_out, int32_t *policy_out)
+extern "C" int gw_sgns_auto_shape(int32_t n, int64_t W, int64_t job_walks, int64_t max_start_walks,
+                                  int64_t *lanes_out, int64_t *unit_walks_out, int32_t *policy_out)
 {
     using namespace gw;
     GW_REQUIRE(n > 0 && W > 0 && job_walks > 0 && lanes_out && unit_walks_out && policy_out,
@@ -742,6 +749,10 @@ extern "C" int gw_sgns_auto_shape(int32_t n, int64_t W, int64_t job_walks, int64
     int64_t unit = (int64_t)(0.36 * pow((double)n, 0.75) + 0.5);
     if (unit > kAutoUnitMax) unit = kAutoUnitMax;
     if (unit < kAutoUnitMin) unit = kAutoUnitMin;
+    // max_start_walks = niter * (largest number of distinct neighbours); < 0: unknown, assume hubs
+    // on any corpus large enough to have them
+    const bool hubs = max_start_walks >= 0 ? max_start_walks >= kAutoHubWalks : W >= 100 * kAutoHubWalks;
+    if (hubs && unit < kAutoHubUnitMin) unit = kAutoHubUnitMin;
     if (unit > W) unit = W;
     const int64_t nunits = ceil_div<int64_t>(W, unit);
     if (lanes > nunits) lanes = nunits;

@@ -382,8 +382,9 @@ class DeepWalk(object):
                   _lib.ptr(syn1neg), st)
         job_walks = max(1, int(batch_words) // max(L, 1))
         a_l, a_u, a_p = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int32(0)
-        _lib.call('gw_sgns_auto_shape', n, W, job_walks, ctypes.byref(a_l), ctypes.byref(a_u),
-                  ctypes.byref(a_p))
+        md = getattr(graph, 'max_degree', None) if graph is not None else None
+        _lib.call('gw_sgns_auto_shape', n, W, job_walks, -1 if md is None else int(md) * wc.niter,
+                  ctypes.byref(a_l), ctypes.byref(a_u), ctypes.byref(a_p))
         if int(lanes) == 0:
             lanes = a_l.value
         if int(unit_walks) == 0:

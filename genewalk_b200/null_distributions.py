@@ -100,7 +100,9 @@ def get_rand_graph(mg, seed=None, materialize=True, degrees=None):
                   _lib.ptr(row_ptr), _lib.ptr(col_idx), ctypes.byref(nnz), st)
     # the node labels are numbers which gives problems in word2vec so adjust 0 to n0 (:26-29)
     nodes = ['n%s' % i for i in range(n)]
-    csr = GraphCSR.from_device(nodes, row_ptr, col_idx, nnz.value)
+    # multigraph degree of the first (largest) node: an upper bound of its distinct neighbours
+    csr = GraphCSR.from_device(nodes, row_ptr, col_idx, nnz.value,
+                               max_degree=int(d_seq[0]) if n > 0 else 0)
     dg = DeviceGraph(csr, edge_u, edge_v)
     return dg.to_networkx() if materialize else dg
 

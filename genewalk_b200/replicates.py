@@ -137,7 +137,7 @@ def exchange_results(local_sims, local_null, nreps_graph, nreps_null, m, device,
 DEFAULT_CONCURRENT = 24   # upper bound of the replicates in flight per GPU
 
 
-def fit_concurrent(requested, n, vector_size=8, walks=None, lanes=0):
+def fit_concurrent(requested, n, vector_size=8, walks=None, lanes=0, max_start_walks=-1):
     """Replicates to keep in flight at once: at most ``requested``, at most as many trainings as
     are RESIDENT on the GPU together with the workers each of them gets (``lanes``, default: the
     library's shape for an ``n``-node network) -- so that every training really runs with its full
@@ -151,7 +151,7 @@ def fit_concurrent(requested, n, vector_size=8, walks=None, lanes=0):
     if not lanes:
         a_l, a_u, a_p = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int32(0)
         _lib.call('gw_sgns_auto_shape', int(n), int(walks) if walks else 100 * int(n), 1000,
-                  ctypes.byref(a_l), ctypes.byref(a_u), ctypes.byref(a_p))
+                  int(max_start_walks), ctypes.byref(a_l), ctypes.byref(a_u), ctypes.byref(a_p))
         lanes = a_l.value
     resident = int(lib.gw_sgns_resident_trainings(int(vector_size), int(lanes)))
     per_replicate = int(n) * (2 * 4 * int(vector_size) + 64) + (64 << 20)
@@ -326,14 +326,14 @@ def run_walks_many(graph, n_replicates, base_seed=None, concurrent=DEFAULT_CONCU
     if base_seed is None:
         base_seed = random.getrandbits(64)
     csr = _csr_of(graph).to_device()
-    out = []
+    out = [None] * n_replicates          # replicates complete in any order, results keep theirs
 
     def enqueue(rep):
         return real_replicate(csr, base_seed, rep, vector_size, walk_length, niter, wait=False, **w2v)
 
     def finish(rep, dw):
         dw.finish_word2vec()
-        out.append(dw)
+        out[rep] = dw
     nstreams = fit_concurrent(concurrent, csr.n, vector_size, niter * csr.nnz, w2v.get('lanes', 0))
     if min(nstreams, n_replicates) > 1:
         preload_kernels(vector_size, **w2v)
@@ -348,13 +348,13 @@ def null_replicates_many(mg, n_replicates, base_seed=None, concurrent=DEFAULT_CO
     _lib.require_cuda()
     if base_seed is None:
         base_seed = random.getrandbits(64)
-    out = []
+    out = [None] * n_replicates
 
     def enqueue(rep):
         return _NullJob(mg, base_seed, rep, vector_size, walk_length, niter, dict(w2v), degrees=degrees)
 
     def finish(rep, job):
-        out.append((job.dw, job.finish(keep_model=keep_model).cpu().numpy()))
+        out[rep] = (job.dw, job.finish(keep_model=keep_model).cpu().numpy())
     degrees = multigraph_degrees(mg)
     nstreams = fit_concurrent(concurrent, len(degrees), vector_size, niter * int(degrees.sum()),
                               w2v.get('lanes', 0))

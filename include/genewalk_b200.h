@@ -183,10 +183,12 @@ int gw_sgns_train(int32_t n, int32_t d, const int32_t *tokens, const int32_t *ro
                   int64_t lanes, int32_t flags, gw_stream_t stream);
 
 /* The default (lanes, unit_walks, policy) of a training (host pointers).  A function of the
- * network alone: it does not depend on how many trainings share the GPU, nor on how many GPUs the
- * replicates are spread over, so a seed gives the same statistics at every GPU count. */
-int gw_sgns_auto_shape(int32_t n, int64_t W, int64_t job_walks, int64_t *lanes_out,
-                       int64_t *unit_walks_out, int32_t *policy_out);
+ * network alone (n, W and max_start_walks = niter * the largest number of distinct neighbours of a
+ * node, i.e. the longest run of walks with one start node; pass -1 when unknown): it does not
+ * depend on how many trainings share the GPU, nor on how many GPUs the replicates are spread over,
+ * so a seed gives the same statistics at every GPU count. */
+int gw_sgns_auto_shape(int32_t n, int64_t W, int64_t job_walks, int64_t max_start_walks,
+                       int64_t *lanes_out, int64_t *unit_walks_out, int32_t *policy_out);
 
 /* How many trainings of `lanes` workers (vector size d) are resident on the current device at
  * once: the replicate driver keeps at most that many in flight, so that every training really runs

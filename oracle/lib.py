@@ -205,12 +205,14 @@ def gensim_job_seeds(njobs_total, seed=1):
 
 
 def word2vec_gensim_like(tokens, n, d=8, K=5, epochs=5, alpha0=0.025, alpha_min=0.0001,
-                         job_walks=1000, seed=1, nthreads=1):
+                         job_walks=1000, seed=1, nthreads=1, inplace=False):
     """Whole Word2Vec(sentences=walks, sg=1, vector_size=d, window=1, min_count=1, negative=K,
     sample=0) as genewalk/deepwalk.py:135-139 runs it.  Returns (index_to_node, vectors[V', d])."""
     index_to_node, node_to_index, counts = gensim_vocab(tokens, n)
     V = len(index_to_node)
-    tok_idx = np.empty(np.shape(tokens), dtype=np.int32)
+    # inplace: overwrite the caller's int32 token array with vocabulary indices (a human-scale
+    # corpus is 6-8 GB; the study runs several oracle processes side by side)
+    tok_idx = tokens if inplace else np.empty(np.shape(tokens), dtype=np.int32)
     for i, row in enumerate(np.asarray(tokens)):
         tok_idx[i] = node_to_index[row]
     cum = gensim_cum_table(counts)

@@ -480,14 +480,20 @@ def test_sgns_hogwild_close_to_sequential():
 def test_sgns_auto_shape():
     """The default shape is a function of the network alone (never of GPU fill or GPU count)."""
     lanes, unit, policy = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int32(0)
-    seen = []
-    for n, W in ((2300, 3465000), (38000, 152681600), (1000000, 1000000000), (3, 400)):
-        _lib.call('gw_sgns_auto_shape', n, W, 1000, ctypes.byref(lanes), ctypes.byref(unit),
+
+    def shape(n, W, hub):
+        _lib.call('gw_sgns_auto_shape', n, W, 1000, hub, ctypes.byref(lanes), ctypes.byref(unit),
                   ctypes.byref(policy))
-        assert 1 <= lanes.value <= max(1, n // 2) and unit.value >= 1 and policy.value in (0, 1)
-        assert lanes.value * unit.value <= max(W, unit.value)
-        seen.append(lanes.value)
-    assert seen[0] <= seen[1] <= seen[2]
+        return lanes.value, unit.value, policy.value
+    assert shape(2300, 3465000, 36100) == (95, 120, 0)            # C1: no hubs, short units
+    assert shape(8500, 45109200, 192800) == (354, 320, 0)         # hubs: units of >= 320 walks
+    assert shape(38000, 152681600, 729700) == (1536, 980, 0)      # C2
+    assert shape(38000, 152681600, -1) == (1536, 980, 0)          # hub size unknown
+    assert shape(1000000, 1000000000, 497900) == (1536, 1000, 0)  # C5
+    assert shape(3, 400, 200)[0] == 1
+    for n, W in ((2300, 3465000), (38000, 152681600), (1000000, 1000000000), (3, 400)):
+        l, u, p = shape(n, W, -1)
+        assert 1 <= l <= max(1, n // 2) and u >= 1 and p in (0, 1) and l * u <= max(W, u)
     lib = _lib.load()
     assert lib.gw_sgns_resident_trainings(8, 1536) == 148 * 128 // 1536
     assert lib.gw_sgns_resident_trainings(8, 1) >= 1024 and lib.gw_sgns_resident_trainings(128, 10 ** 6) == 1

@@ -52,8 +52,13 @@ def runs():
         z = np.load(f)
         seed, nreps = int(z['seed']), int(z['nreps'])
         mg, genes = workloads.modular_gene_go_network(seed=100 + seed)     # tools/parity_study.build_case
+        # GW_PARITY_SHAPE=lanes:unit_walks overrides the shipped default (shape studies only)
+        shape = os.environ.get('GW_PARITY_SHAPE')
+        kw = dict(zip(('lanes', 'unit_walks'), map(int, shape.split(':')))) if shape else {}
+        if os.environ.get('GW_PARITY_REDUCTIONS'):
+            kw['reductions'] = os.environ['GW_PARITY_REDUCTIONS']
         df, parts = run_genewalk(mg, genes, nreps_graph=nreps, nreps_null=nreps, alpha_fdr=1,
-                                 gene_id_type='custom', base_seed=seed, return_parts=True)
+                                 gene_id_type='custom', base_seed=seed, return_parts=True, **kw)
         rows = df[df['go_id'] != '']
         nodes = list(mg.nodes())
         key = {(nodes[g], nodes[t]): k for k, (g, t) in enumerate(zip(z['pair_gene'], z['pair_go']))}

@@ -181,7 +181,7 @@ def test_fit_concurrent_caps_by_residency_and_memory(monkeypatch):
             return max(1, 148 * 512 // (lanes * (d // 2)))
     monkeypatch.setattr(_lib, 'load', lambda: FakeLib)
 
-    def fake_call(name, n, W, job, lanes, unit, policy):
+    def fake_call(name, n, W, job, hub, lanes, unit, policy):
         assert name == 'gw_sgns_auto_shape'
         lanes._obj.value = max(16, min(1536, n // 24))
     monkeypatch.setattr(_lib, 'call', fake_call)

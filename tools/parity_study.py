@@ -79,7 +79,8 @@ def oracle_vectors(row_ptr, col_idx, walk_seed, sgns_seed, mode, nthreads=1):
     n = len(row_ptr) - 1
     if mode == 'gensim':      # reference restatement: corpus order, cum_table + LCG, job alpha
         tok = olib.walk_uniform(row_ptr, col_idx, NITER, WL, walk_seed, 0)
-        itn, syn0, _ = olib.word2vec_gensim_like(tok, n, d=D, K=K, epochs=EPOCHS, nthreads=nthreads)
+        itn, syn0, _ = olib.word2vec_gensim_like(tok, n, d=D, K=K, epochs=EPOCHS, nthreads=nthreads,
+                                                 inplace=True)
         vec = np.zeros((n, D), dtype=np.float32)
         vec[itn] = syn0
         return vec
