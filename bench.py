@@ -561,7 +561,7 @@ def main():
     ap.add_argument('--no-pipeline', action='store_true')
     ap.add_argument('--no-l2-peak', action='store_true')
     args = ap.parse_args()
-    default_reps = {'c2': (10, 10), 'c4': (6, 6), 'c5': (6, 6)}[args.config]
+    default_reps = {'c2': (10, 10), 'c4': (6, 6), 'c5': (2, 2)}[args.config]
     if args.real is None:
         args.real = default_reps[0]
     if args.null is None:

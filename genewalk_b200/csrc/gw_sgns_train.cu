@@ -70,6 +70,9 @@ struct TrainParams {
 constexpr int64_t kAutoLanesMax = 1536;
 constexpr int64_t kAutoLanesMin = 16;
 constexpr int64_t kAutoRowsPerLane = 24;
+constexpr int64_t kAutoLargeN = 200000;
+constexpr int64_t kAutoLargeRowsPerLane = 128;
+constexpr int64_t kAutoLargeLanesMax = 8192;
 constexpr int64_t kAutoUnitMin = 50;
 constexpr int64_t kAutoUnitMax = 1000;
 constexpr int64_t kAutoHubWalks = 100000;
@@ -744,6 +747,14 @@ extern "C" int gw_sgns_auto_shape(int32_t n, int64_t W, int64_t job_walks, int64
                "gw_sgns_auto_shape: bad arguments");
     int64_t lanes = n / kAutoRowsPerLane;
     if (lanes > kAutoLanesMax) lanes = kAutoLanesMax;
+    // beyond the validated range (n <= 38k): one worker per 128 rows, so that the trainings that
+    // fill the GPU are few enough for their tables (64 B per row and training) to stay in L2.
+    // Extrapolated from the window rule (workers x unit ~ 0.75 % of the corpus); no oracle exists
+    // at this size (28 CPU-hours per replicate).
+    if (n >= kAutoLargeN && (int64_t)n / kAutoLargeRowsPerLane > lanes) {
+        lanes = (int64_t)n / kAutoLargeRowsPerLane;
+        if (lanes > kAutoLargeLanesMax) lanes = kAutoLargeLanesMax;
+    }
     if (lanes < kAutoLanesMin) lanes = kAutoLanesMin;
     if (lanes > n / 2) lanes = n / 2 > 0 ? n / 2 : 1;
     int64_t unit = (int64_t)(0.36 * pow((double)n, 0.75) + 0.5);

@@ -57,6 +57,9 @@ def main():
     ap.add_argument('--nreps', type=int, default=10)
     ap.add_argument('--src', default='gpurun_out/parity10')
     ap.add_argument('--dst', default=os.path.join(ROOT, 'tests', 'golden'))
+    ap.add_argument('--compact', action='store_true',
+                    help='large networks: store the significant set as packed bits and the mean '
+                         'similarities as float16, no pair index arrays (the test recomputes the pairs)')
     a = ap.parse_args()
     from scipy.stats import ks_2samp
     from oracle import stats_ref
@@ -68,10 +71,16 @@ def main():
         D = load_side(a.src, a.case, 'oracle-device', seed, a.nreps)
         assert G is not None, 'oracle-gensim outputs missing for seed %d' % seed
         padj_g = stats_ref.gene_padj(G[0], G[1], seg)
-        out = dict(case=a.case, seed=seed, nreps=a.nreps, pair_gene=pg.astype(np.int32),
-                   pair_go=po.astype(np.int32), seg_ptr=seg, null_q=quantiles(G[1]),
-                   null_mean=float(G[1].mean()), null_sd=float(G[1].std()), n_null=len(G[1]),
-                   sims_mean=G[0].mean(axis=0).astype(np.float32), gene_padj=padj_g)
+        if a.compact:
+            out = dict(case=a.case, seed=seed, nreps=a.nreps, m=len(po), null_q=quantiles(G[1]),
+                       null_mean=float(G[1].mean()), null_sd=float(G[1].std()), n_null=len(G[1]),
+                       sims_mean=G[0].mean(axis=0).astype(np.float16),
+                       sig_bits=np.packbits(padj_g < 0.1))
+        else:
+            out = dict(case=a.case, seed=seed, nreps=a.nreps, pair_gene=pg.astype(np.int32),
+                       pair_go=po.astype(np.int32), seg_ptr=seg, null_q=quantiles(G[1]),
+                       null_mean=float(G[1].mean()), null_sd=float(G[1].std()), n_null=len(G[1]),
+                       sims_mean=G[0].mean(axis=0).astype(np.float32), gene_padj=padj_g)
         if D is not None:
             padj_d = stats_ref.gene_padj(D[0], D[1], seg)
             sg, sd = padj_g < 0.1, padj_d < 0.1

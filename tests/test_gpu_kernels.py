@@ -489,7 +489,8 @@ def test_sgns_auto_shape():
     assert shape(8500, 45109200, 192800) == (354, 320, 0)         # hubs: units of >= 320 walks
     assert shape(38000, 152681600, 729700) == (1536, 980, 0)      # C2
     assert shape(38000, 152681600, -1) == (1536, 980, 0)          # hub size unknown
-    assert shape(1000000, 1000000000, 497900) == (1536, 1000, 0)  # C5
+    assert shape(1000000, 1000000000, 497900) == (7812, 1000, 0)  # C5: tables of few trainings fit L2
+    assert shape(50000, 977650800, 1836900) == (1536, 1000, 0)    # C4
     assert shape(3, 400, 200)[0] == 1
     for n, W in ((2300, 3465000), (38000, 152681600), (1000000, 1000000000), (3, 400)):
         l, u, p = shape(n, W, -1)

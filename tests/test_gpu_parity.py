@@ -104,3 +104,41 @@ def test_significant_pairs_jaccard(runs):
 def test_similarities_close(runs):
     for r in runs:
         assert r['dsim'] <= DSIM_FLOOR_FACTOR * r['floor_dsim'] + 0.005, r
+
+
+# ---- the bench workload (C2, human scale) at nreps 3/3 -------------------------------------------
+C2_FIXTURE = os.path.join(GOLD, 'parity_c2_s0.npz')
+C2_KS_MAX = 0.03
+C2_JACCARD_MIN = 0.80
+
+
+@pytest.mark.skipif(not os.path.exists(C2_FIXTURE), reason='C2 parity fixture not generated')
+def test_c2_parity_nreps3():
+    """Shipped defaults on BASELINE.json configs[1] (38k nodes, 1.5 M adjacency entries) with
+    nreps_graph = nreps_null = 3 against three + three SEQUENTIAL oracle replicates of the same
+    seeds (fixture: 27 CPU-hours, tests/golden/make_parity_fixture.py --case c2 --nreps 3 --compact).
+    No oracle-vs-oracle floor exists at this size; the thresholds are the C1 KS bar and a Jaccard
+    bar below the measured value (profiles/parity_study_r02.md)."""
+    from oracle import stats_ref
+    from genewalk_b200.perform_statistics import GeneWalk
+    z = np.load(C2_FIXTURE)
+    n, u, v, is_go = workloads.human_scale_edges(seed=2 + int(z['seed']))
+    mg, genes = workloads.edges_to_networkx(n, u, v, is_go, 20000)
+    nreps = int(z['nreps'])
+    df, parts = run_genewalk(mg, genes, nreps_graph=nreps, nreps_null=nreps, alpha_fdr=1,
+                             gene_id_type='custom', base_seed=int(z['seed']), return_parts=True)
+    pairs = GeneWalk(mg, genes, [], np.zeros(1, np.float32), gene_id_type='custom').collect_pairs()
+    m = int(z['m'])
+    assert len(pairs['pair_go']) == m
+    sims = parts['sims'].cpu().numpy()
+    padj = stats_ref.gene_padj(sims, parts['null'], pairs['seg_ptr'])
+    sig = padj < 0.1
+    sig_ref = np.unpackbits(z['sig_bits'])[:m].astype(bool)
+    ks = ks_against_quantiles(z['null_q'], parts['null'])
+    jac = float((sig & sig_ref).sum() / max(1, (sig | sig_ref).sum()))
+    dsim = float(np.abs(sims.mean(axis=0) - z['sims_mean'].astype(np.float32)).mean())
+    print('C2 parity nreps %d: KS %.4f  null mean %.4f vs %.4f  Jaccard %.4f  nsig %d vs %d  |dsim| %.4f' % (
+        nreps, ks, parts['null'].mean(), float(z['null_mean']), jac, sig.sum(), sig_ref.sum(), dsim))
+    assert ks <= C2_KS_MAX
+    assert abs(float(parts['null'].mean()) - float(z['null_mean'])) <= 0.015
+    assert jac >= C2_JACCARD_MIN

@@ -3,7 +3,7 @@ KS agreement of the null similarity distributions, Jaccard of FDR-significant ge
 
   python tools/parity_study.py --side oracle --mode gensim  --out gpurun_out/study   (CPU, here)
   python tools/parity_study.py --side oracle --mode device  --out gpurun_out/study   (CPU, here)
-  python tools/parity_study.py --side gpu --conc 2048,16384,0 --out gpurun_out/study (B200 box)
+  python tools/parity_study.py --side gpu --tag default --out gpurun_out/study      (B200 box)
   python tools/parity_study.py --side compare --out gpurun_out/study
 
 Both sides regenerate the same corpora from the same seeds (walks and randomized graphs are
@@ -135,43 +135,34 @@ def run_oracle(a):
 
 # ---------------------------------------------------------------------------------------------
 def run_gpu(a):
+    """GPU side: nreps real + nreps null replicates per seed with the given trainer shape
+    (0 = library default); `tools/parity_sweep.py` is the many-shapes-in-one-process variant."""
     import torch
     from genewalk_b200.deepwalk import DeepWalk
     from genewalk_b200.null_distributions import get_rand_graph, get_null_distributions
     from genewalk_b200.perform_statistics import GeneWalk
     from genewalk_b200.csr import GraphCSR
-    timings = {}
+    kw = dict(lanes=a.conc[0], unit_walks=a.chunk, reductions=a.reductions)
+    tag = a.tag or 'default'
     for seed in a.seeds:
         mg, genes = build_case(a.case, seed)
         csr = GraphCSR.from_networkx(mg)
         gw = GeneWalk(mg, genes, [], np.zeros(1, np.float32), gene_id_type='custom')
         pairs = gw.collect_pairs()
-        for conc in a.conc:
-            for rep in range(a.nreps):
-                torch.cuda.synchronize(); t0 = time.time()
-                dw = DeepWalk(csr, WL, NITER, seed=mix(seed, 0, rep))
-                dw.get_walks()
-                dw.word2vec(vector_size=D, negative=K, epochs=EPOCHS, sgns_seed=mix(seed, 1 + 16 * a.salt, rep),
-                            lanes=conc, chunk_walks=a.chunk, streams=a.streams, reductions=a.reductions)
-                sims = gw.pair_similarities(dw.model.wv, pairs).cpu().numpy()
-                torch.cuda.synchronize(); dt = time.time() - t0
-                np.save(os.path.join(a.out, '%s_gpu-%s%d_s%d_real%d.npy' % (a.case, a.tag, conc, seed, rep)), sims)
-                del dw
-                t1 = time.time()
-                rg = get_rand_graph(mg, seed=mix(seed, 2, rep), materialize=False)
-                dw = DeepWalk(rg, WL, NITER, seed=mix(seed, 3, rep))
-                dw.get_walks()
-                dw.word2vec(vector_size=D, negative=K, epochs=EPOCHS, sgns_seed=mix(seed, 4 + 16 * a.salt, rep),
-                            lanes=conc, chunk_walks=a.chunk, streams=a.streams, reductions=a.reductions)
-                null = np.asarray(get_null_distributions(rg, dw.model.wv), dtype=np.float32)
-                torch.cuda.synchronize(); dt2 = time.time() - t1
-                np.save(os.path.join(a.out, '%s_gpu-%s%d_s%d_null%d.npy' % (a.case, a.tag, conc, seed, rep)), null)
-                del dw, rg
-                timings['%d/%d/%d' % (conc, seed, rep)] = [dt, dt2]
-                print('gpu conc=%d seed %d rep %d: real %.2fs null %.2fs' % (conc, seed, rep, dt, dt2),
-                      flush=True)
-    with open(os.path.join(a.out, '%s_gpu_timings.json' % a.case), 'w') as f:
-        json.dump(timings, f)
+        for rep in range(a.nreps):
+            dw = DeepWalk(csr, WL, NITER, seed=mix(seed, 0, rep))
+            dw.get_walks()
+            dw.word2vec(vector_size=D, negative=K, epochs=EPOCHS, sgns_seed=mix(seed, 1 + 16 * a.salt, rep), **kw)
+            sims = gw.pair_similarities(dw.model.wv, pairs).cpu().numpy()
+            np.save(os.path.join(a.out, '%s_gpu-%s_s%d_real%d.npy' % (a.case, tag, seed, rep)), sims)
+            rg = get_rand_graph(mg, seed=mix(seed, 2, rep), materialize=False)
+            dw = DeepWalk(rg, WL, NITER, seed=mix(seed, 3, rep))
+            dw.get_walks()
+            dw.word2vec(vector_size=D, negative=K, epochs=EPOCHS, sgns_seed=mix(seed, 4 + 16 * a.salt, rep), **kw)
+            null = np.asarray(get_null_distributions(rg, dw.model.wv), dtype=np.float32)
+            np.save(os.path.join(a.out, '%s_gpu-%s_s%d_null%d.npy' % (a.case, tag, seed, rep)), null)
+            torch.cuda.synchronize()
+            print('gpu %s seed %d rep %d done' % (tag, seed, rep), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -225,11 +216,10 @@ def main():
     ap.add_argument('--case', default='c1mod')
     ap.add_argument('--seeds', default='0,1,2')
     ap.add_argument('--nreps', type=int, default=2)
-    ap.add_argument('--conc', default='0')
-    ap.add_argument('--chunk', type=int, default=0)
-    ap.add_argument('--streams', type=int, default=0)
+    ap.add_argument('--conc', default='0', help='gpu side: workers per training (0 = library default)')
+    ap.add_argument('--chunk', type=int, default=0, help='gpu side: walks per unit (0 = library default)')
     ap.add_argument('--tag', default='')
-    ap.add_argument('--reductions', default='auto')
+    ap.add_argument('--reductions', default='per_pair')
     ap.add_argument('--salt', type=int, default=0, help='gpu side: perturb only the negative-sampling seeds')
     ap.add_argument('--procs', type=int, default=os.cpu_count())
     ap.add_argument('--out', default='gpurun_out/study')
