@@ -463,7 +463,7 @@ def run_ours(args):
         a_l, a_u, a_p = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int32(0)
         _lib.call('gw_sgns_auto_shape', n, NITER * A, 1000, NITER * int(csr.max_degree or 0),
                   ctypes.byref(a_l), ctypes.byref(a_u), ctypes.byref(a_p))
-        mix, gat, src = live_l2_peak(2 * R * n) if not args.no_l2_peak else (None, None, 'skipped')
+        mix, gat, src = live_l2_peak(2 * in_flight * n) if not args.no_l2_peak else (None, None, 'skipped')
         steps_per_s = walks_timed * PAIRS_PER_WALK / 2 / (busy_ms / 1e3)   # step = 2 pairs (13 gathers + 14 reductions)
         if mix is None:
             try:
