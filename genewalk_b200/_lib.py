@@ -33,7 +33,7 @@ SIGNATURES = {
     'gw_alias_build': [_i32, _vp, _f64, _vp, _vp],
     'gw_sgns_init': [_i32, _i32, _vp, _vp, _vp, _vp, _vp],
     'gw_walk_count': [_i32, _i64, _vp, _vp, _i32, _i32, _u64, _vp, _vp],
-    'gw_sgns_plan': [_i32, _vp, _i32, _i64, _i64, _i32, _vp, _i64, _vp, _vp],
+    'gw_sgns_plan': [_i32, _vp, _i32, _i64, _i64, _i32, _i64, _vp, _i64, _vp, _vp],
     'gw_sgns_train': [_i32, _i32, _vp, _vp, _vp, _i32, _u64, _i64, _i32, _i32, _i32, _i32, _i32, _i32,
                       _f64, _f64, _i64, _vp, _vp, _vp, _vp, _vp, _u64, _i64, _i32, _vp],
     'gw_sgns_auto_shape': [_i32, _i64, _i64, _i64, ctypes.POINTER(_i64), ctypes.POINTER(_i64),

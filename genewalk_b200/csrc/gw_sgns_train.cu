@@ -664,12 +664,14 @@ __global__ void plan_chunk_kernel(int32_t n, const int32_t *__restrict__ row_ptr
 }
 
 __global__ void plan_burst_count_kernel(int32_t n, const int32_t *__restrict__ row_ptr, int32_t niter,
-                                        int64_t unit_walks, int64_t *__restrict__ pieces)
+                                        int64_t unit_walks, int64_t max_pieces, int64_t *__restrict__ pieces)
 {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n) return;
     const int64_t len = (int64_t)(row_ptr[v + 1] - row_ptr[v]) * niter;
-    pieces[v] = len == 0 ? 0 : ceil_div<int64_t>(len, unit_walks);
+    int64_t k = len == 0 ? 0 : ceil_div<int64_t>(len, unit_walks);
+    if (max_pieces > 0 && k > max_pieces) k = max_pieces;   // a hub's walks: at most max_pieces workers
+    pieces[v] = k;
 }
 
 __global__ void plan_burst_fill_kernel(int32_t n, const int32_t *__restrict__ row_ptr, int32_t niter,
@@ -705,13 +707,14 @@ extern "C" int64_t gw_sgns_plan_capacity(int32_t n, int64_t W, int64_t unit_walk
 }
 
 extern "C" int gw_sgns_plan(int32_t n, const int32_t *row_ptr, int32_t niter, int64_t W, int64_t unit_walks,
-                            int32_t policy, gw_sgns_unit *units, int64_t capacity, int64_t *num_units,
-                            gw_stream_t stream)
+                            int32_t policy, int64_t max_pieces, gw_sgns_unit *units, int64_t capacity,
+                            int64_t *num_units, gw_stream_t stream)
 {
     using namespace gw;
     cudaStream_t s = (cudaStream_t)stream;
-    GW_REQUIRE(units && num_units && W > 0 && unit_walks >= 1 && unit_walks < ((int64_t)1 << 31),
+    GW_REQUIRE(units && num_units && W > 0 && unit_walks >= 1 && unit_walks < ((int64_t)1 << 31) && max_pieces >= 0,
                "gw_sgns_plan: bad arguments");
+    GW_REQUIRE(max_pieces == 0 || W / max_pieces < ((int64_t)1 << 31), "gw_sgns_plan: max_pieces too small for W");
     GW_REQUIRE(capacity >= gw_sgns_plan_capacity(n, W, unit_walks, policy),
                "gw_sgns_plan: capacity %lld < gw_sgns_plan_capacity()", (long long)capacity);
     if (policy == GW_PLAN_CHUNK) {
@@ -727,7 +730,7 @@ extern "C" int gw_sgns_plan(int32_t n, const int32_t *row_ptr, int32_t niter, in
     GW_CUDA_OK(pieces.alloc(sizeof(int64_t) * (size_t)n, s));
     GW_CUDA_OK(total.alloc(sizeof(int64_t), s));
     const unsigned grid = (unsigned)ceil_div<int64_t>(n, 256);
-    plan_burst_count_kernel<<<grid, 256, 0, s>>>(n, row_ptr, niter, unit_walks, pieces.as<int64_t>());
+    plan_burst_count_kernel<<<grid, 256, 0, s>>>(n, row_ptr, niter, unit_walks, max_pieces, pieces.as<int64_t>());
     GW_LAUNCH_OK();
     GW_TRY(scan_exclusive_i64(pieces.as<int64_t>(), pieces.as<int64_t>(), n, total.as<int64_t>(), s));
     plan_burst_fill_kernel<<<grid, 256, 0, s>>>(n, row_ptr, niter, pieces.as<int64_t>(), total.as<int64_t>(),

@@ -263,7 +263,7 @@ class DeepWalk(object):
         gensim's ``workers``; 0 = library default, a function of the network only; 1 =
         sequential), ``unit_walks`` and ``policy`` ('chunk' | 'burst': how the corpus is cut into
         the units the workers take from the queue, see ``gw_sgns_plan``; 0 / None = library
-        default), ``reductions`` ('per_pair' | 'merged': see ``gw_sgns_flags`` in
+        default; ``max_pieces`` caps the workers per start node of a 'burst' plan), ``reductions`` ('per_pair' | 'merged': see ``gw_sgns_flags`` in
         include/genewalk_b200.h), ``wait`` (False: only enqueue the training on the current CUDA
         stream; ``finish_word2vec()`` then downloads the vectors), ``sgns_seed`` (Philox key of
         the negative draws) and ``epoch_hook`` (see ``train_device``).
@@ -280,6 +280,7 @@ class DeepWalk(object):
         lanes = int(kwargs.pop('lanes', 0))
         unit_walks = int(kwargs.pop('unit_walks', 0))
         policy = kwargs.pop('policy', None)
+        max_pieces = int(kwargs.pop('max_pieces', 0))
         reductions = kwargs.pop('reductions', 'per_pair')
         kwargs_async = not bool(kwargs.pop('wait', True))
         sgns_seed = kwargs.pop('sgns_seed', None)
@@ -306,6 +307,7 @@ class DeepWalk(object):
                                           alpha=alpha, min_alpha=min_alpha, init_seed=init_seed,
                                           ns_exponent=ns_exponent, batch_words=batch_words,
                                           lanes=lanes, unit_walks=unit_walks, policy=policy,
+                                          max_pieces=max_pieces,
                                           reductions=reductions, sgns_seed=sgns_seed,
                                           epoch_hook=epoch_hook)
         if kwargs_async:
@@ -337,7 +339,7 @@ class DeepWalk(object):
 
     def train_device(self, vector_size=8, negative=5, epochs=5, alpha=0.025, min_alpha=0.0001,
                      init_seed=1, ns_exponent=0.75, batch_words=10000, lanes=0, unit_walks=0,
-                     policy=None, reductions='per_pair', sgns_seed=None, epoch_hook=None):
+                     policy=None, max_pieces=0, reductions='per_pair', sgns_seed=None, epoch_hook=None):
         """Enqueue vocabulary, alias table, init and the SGNS epochs on the current stream and
         return the device tensors (no host synchronisation).  ``epoch_hook(stage, when)`` is called
         with when in {'before', 'after'} around the vocabulary pass (stage 'count') and around every
@@ -397,7 +399,8 @@ class DeepWalk(object):
         units = torch.empty((cap, 2), dtype=torch.int64, device=dev)    # gw_sgns_unit[cap]
         num_units = torch.zeros(1, dtype=torch.int64, device=dev)
         _lib.call('gw_sgns_plan', n, _lib.ptr(graph.d_row_ptr) if graph is not None else None,
-                  wc.niter if wc is not None else 1, W, int(unit_walks), policy_id, _lib.ptr(units), cap,
+                  wc.niter if wc is not None else 1, W, int(unit_walks), policy_id, int(max_pieces),
+                  _lib.ptr(units), cap,
                   _lib.ptr(num_units), st)
         flags = {'per_pair': 0, 'merged': 4}[reductions]
         regen = tokens is None

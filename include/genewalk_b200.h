@@ -132,17 +132,20 @@ typedef struct {
  *                  jobs; a unit may span several start nodes;
  *   GW_PLAN_BURST  a unit never crosses a start node: the niter*len(graph[v]) walks that start at v
  *                  (deepwalk.py:67-70,197) are one unit, cut into ceil(len/unit_walks) near-equal
- *                  pieces when longer than unit_walks. */
+ *                  pieces when longer than unit_walks -- but into at most max_pieces (> 0) pieces, so
+ *                  that no more than max_pieces workers ever train walks of one start node at the
+ *                  same time (a hub's rows overshoot when too many stale updates meet in them). */
 enum gw_plan_policy { GW_PLAN_CHUNK = 0, GW_PLAN_BURST = 1 };
 
 /* number of gw_sgns_unit entries gw_sgns_plan may write (host-side arithmetic) */
 int64_t gw_sgns_plan_capacity(int32_t n, int64_t W, int64_t unit_walks, int32_t policy);
 
 /* Writes the units of a W = niter*A walk corpus in corpus order and *num_units (device int64).
- * row_ptr may be NULL for GW_PLAN_CHUNK (corpora that do not come from gw_walk_uniform). */
+ * row_ptr may be NULL for GW_PLAN_CHUNK (corpora that do not come from gw_walk_uniform);
+ * max_pieces (0 = unlimited) applies to GW_PLAN_BURST. */
 int gw_sgns_plan(int32_t n, const int32_t *row_ptr, int32_t niter, int64_t W, int64_t unit_walks,
-                 int32_t policy, gw_sgns_unit *units, int64_t capacity, int64_t *num_units,
-                 gw_stream_t stream);
+                 int32_t policy, int64_t max_pieces, gw_sgns_unit *units, int64_t capacity,
+                 int64_t *num_units, gw_stream_t stream);
 
 /* Trains epochs [epoch_begin, epoch_end) of `epochs` over the W walks of the corpus (window 1), in
  * the corpus order the learning-rate schedule refers to (for GeneWalk: the reference's node-major

@@ -246,14 +246,14 @@ def sgns_case(n, m, niter, L, d, K, epochs, seed):
     return tok, prob, alias, syn0, syn1
 
 
-def gpu_plan(n, W, unit_walks, policy, row_ptr=None, niter=1):
+def gpu_plan(n, W, unit_walks, policy, row_ptr=None, niter=1, max_pieces=0):
     """gw_sgns_plan -> (device units tensor, device num_units, host copy of the units)."""
     lib = _lib.load()
     cap = int(lib.gw_sgns_plan_capacity(n, W, unit_walks, policy))
     units = torch.empty((cap, 2), dtype=torch.int64, device='cuda')
     num = torch.zeros(1, dtype=torch.int64, device='cuda')
     d_rp = dev(row_ptr, np.int32) if row_ptr is not None else None
-    _lib.call('gw_sgns_plan', n, _lib.ptr(d_rp), niter, W, unit_walks, policy, _lib.ptr(units), cap,
+    _lib.call('gw_sgns_plan', n, _lib.ptr(d_rp), niter, W, unit_walks, policy, max_pieces, _lib.ptr(units), cap,
               _lib.ptr(num), st())
     torch.cuda.synchronize()
     k = int(num.item())
@@ -375,6 +375,12 @@ def test_sgns_plan_units():
             big = np.argmax(burst)
             c = u['count'][u['node'] == big]
             assert c.max() - c.min() <= 1
+    # hub cap: no start node is cut into more than max_pieces units
+    _, _, u = gpu_plan(n, W, 25, 1, row_ptr, niter, max_pieces=7)
+    assert u['first'][-1] + u['count'][-1] == W and np.array_equal(u['first'][1:], (u['first'] + u['count'])[:-1])
+    burst = np.diff(row_ptr) * niter
+    assert np.array_equal(np.bincount(u['node'], minlength=n), np.minimum(-(-burst // 25), 7))
+    assert u['count'].max() == -(-burst.max() // 7)
     # a plan without a graph (corpora given as lists of walks)
     _, _, u = gpu_plan(10, 1234, 100, 0, None, 1)
     assert len(u) == 13 and (u['node'] == -1).all() and u['count'][-1] == 34

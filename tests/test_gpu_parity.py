@@ -57,6 +57,9 @@ def runs():
         kw = dict(zip(('lanes', 'unit_walks'), map(int, shape.split(':')))) if shape else {}
         if os.environ.get('GW_PARITY_REDUCTIONS'):
             kw['reductions'] = os.environ['GW_PARITY_REDUCTIONS']
+        for item in filter(None, os.environ.get('GW_PARITY_EXTRA', '').split(',')):   # e.g. policy=burst,max_pieces=384
+            k, v = item.split('=')
+            kw[k] = int(v) if v.isdigit() else v
         df, parts = run_genewalk(mg, genes, nreps_graph=nreps, nreps_null=nreps, alpha_fdr=1,
                                  gene_id_type='custom', base_seed=seed, return_parts=True, **kw)
         rows = df[df['go_id'] != '']

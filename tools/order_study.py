@@ -49,7 +49,7 @@ def order_of_units(first, count, lanes):
 
 
 def units_of(policy, row_ptr, W):
-    kind, lanes, size = policy.split(':')
+    kind, lanes, size = policy.split(':')[:3]
     lanes, size = int(lanes), int(size)
     if kind == 'chunk':
         first = np.arange(0, W, size, dtype=np.int64)
@@ -68,6 +68,20 @@ def units_of(policy, row_ptr, W):
                 k = -(-ln // size)
                 for j in range(k):
                     first.append(s + j * size); count.append(min(size, ln - j * size))
+        first, count = np.array(first, np.int64), np.array(count, np.int64)
+    elif kind == 'burstcap':   # burstcap:lanes:unit:max_pieces -- start-node units, at most max_pieces per node
+        cap = int(policy.split(':')[3])
+        deg = np.diff(row_ptr).astype(np.int64)
+        b0 = row_ptr[:-1].astype(np.int64) * NITER
+        blen = deg * NITER
+        first, count = [], []
+        for s, ln in zip(b0, blen):
+            if ln == 0:
+                continue
+            k = min(-(-ln // size), cap)
+            for j in range(k):
+                a, b = s + (ln * j) // k, s + (ln * (j + 1)) // k
+                first.append(a); count.append(b - a)
         first, count = np.array(first, np.int64), np.array(count, np.int64)
     else:
         raise ValueError(policy)
