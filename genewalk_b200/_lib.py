@@ -4,7 +4,6 @@ There is NO CPU fallback: if the library is missing it is built with nvcc, and i
 no CUDA device is present when a compute entry point is called, the call raises.
 """
 import ctypes
-import os
 
 from . import _build
 

@@ -25,7 +25,7 @@ from collections.abc import Sequence
 import numpy as np
 
 from . import _lib
-from .csr import GraphCSR, coprime_stride
+from .csr import GraphCSR
 from .keyedvectors import NodeVectors, Word2VecModel
 
 logger = logging.getLogger('genewalk.deepwalk')

@@ -13,7 +13,6 @@ import numpy as np
 
 from . import _lib
 from .csr import GraphCSR, multigraph_degrees
-from .keyedvectors import NodeVectors
 
 logger = logging.getLogger('genewalk.get_null_distributions')
 

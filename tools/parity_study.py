@@ -12,7 +12,6 @@ This tool imports oracle/ (it is a checker, like tests/); it is not part of the 
 """
 import argparse
 import glob
-import json
 import os
 import sys
 import time
@@ -75,7 +74,6 @@ def pairs_of(mg, genes):
 # ---------------------------------------------------------------------------------------------
 def oracle_vectors(row_ptr, col_idx, walk_seed, sgns_seed, mode, nthreads=1):
     from oracle import lib as olib
-    from genewalk_b200.csr import coprime_stride
     n = len(row_ptr) - 1
     if mode == 'gensim':      # reference restatement: corpus order, cum_table + LCG, job alpha
         tok = olib.walk_uniform(row_ptr, col_idx, NITER, WL, walk_seed, 0)

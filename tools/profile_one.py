@@ -11,7 +11,6 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-import numpy as np                                   # noqa: E402
 import torch                                         # noqa: E402
 from genewalk_b200 import workloads                  # noqa: E402
 from genewalk_b200.csr import GraphCSR               # noqa: E402
