@@ -97,3 +97,25 @@ def test_bad_format_raises(tmp_path):
     p.write_text('a,b,c\n')
     with pytest.raises(ValueError):
         read_network(str(p), 'csv')
+
+
+def test_cli_loads_sif_full_natively(tmp_path):
+    """genewalk_b200.cli reads a complete custom-id SIF without the reference package
+    (cli.py:195-197 -> nx_mg_assembler.load_network) and would pickle an nx.MultiGraph."""
+    import pickle
+    from genewalk_b200 import cli
+    case = [c for c in SIF['cases'] if c['name'] == 'sif_custom_filter'][0]
+    sif = tmp_path / 'net.sif'
+    sif.write_text('\n'.join(','.join(r) for r in case['rows']))
+    obo = tmp_path / 'go.obo'
+    obo.write_text(SIF['obo'])
+    genes = tmp_path / 'genes.txt'
+    genes.write_text('\n'.join(g['ID'] for g in case['genes']) + '\n')
+    args = cli.build_parser().parse_args(['--project', 'p', '--genes', str(genes), '--id_type', 'custom',
+                                          '--network_source', 'sif_full', '--network_file', str(sif),
+                                          '--go_obo', str(obo), '--base_folder', str(tmp_path)])
+    gene_list, net = cli._load_inputs(args, str(tmp_path))
+    assert gene_list == case['genes'] and list(net.nodes()) == case['nodes']
+    mg = pickle.loads(pickle.dumps(net.to_networkx()))
+    assert {v: list(mg[v]) for v in mg.nodes()} == case['adjacency']
+    assert {v: dict(mg.nodes[v]) for v in mg.nodes() if mg.nodes[v]} == case['attrs']
