@@ -68,3 +68,31 @@ def test_staged_run_writes_reference_file_set(tmp_path):
     a.project = 'q'
     cli.run_main(a)
     assert os.path.exists(os.path.join(tmp, 'q', 'genewalk_results.csv'))
+
+
+@pytest.mark.gpu
+def test_all_stages_from_a_sif_file(tmp_path):
+    """--network_source sif_full --id_type custom: the network file goes straight to CSR arrays
+    (edgelist.py, no networkx, no reference package), the three stages run, and multi_graph.pkl
+    still holds the nx.MultiGraph the reference would have written."""
+    import networkx as nx
+    tmp = str(tmp_path)
+    mg, genes = graphs.modular_gene_go_network(150, 30, 5, 600, 350, 40, seed=4)
+    with open(os.path.join(tmp, 'net.sif'), 'w') as fh:
+        fh.write('\n'.join('%s,%s,%s' % (u, d.get('label', 'x'), v) for u, v, d in mg.edges(data=True)))
+        fh.write('\nUNLISTED1,x,UNLISTED2\n')
+    with open(os.path.join(tmp, 'go.obo'), 'w') as fh:
+        for v, a in mg.nodes(data=True):
+            if 'GO' in a:
+                fh.write('[Term]\nid: %s\nname: %s\nnamespace: %s\n\n' % (v, a['name'], a['domain']))
+    with open(os.path.join(tmp, 'genes.txt'), 'w') as fh:
+        fh.write('\n'.join(g['ID'] for g in genes) + '\n')
+    cli.run_main(_args(tmp, stage='all', network_source='sif_full', network_file=os.path.join(tmp, 'net.sif'),
+                       go_obo=os.path.join(tmp, 'go.obo'), id_type='custom', nreps_graph=2, nreps_null=2,
+                       random_seed=7))
+    proj = os.path.join(tmp, 'p')
+    saved = cli.load_pickle(proj, 'multi_graph')
+    assert isinstance(saved, nx.MultiGraph) and 'UNLISTED1' not in saved
+    assert saved.number_of_edges() == mg.number_of_edges()
+    df = pd.read_csv(os.path.join(proj, 'genewalk_results.csv'))
+    assert df['go_id'].notna().sum() > 100 and df['go_name'].notna().sum() == df['go_id'].notna().sum()
